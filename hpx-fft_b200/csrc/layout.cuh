@@ -1,0 +1,72 @@
+// layout.cuh -- HBM data layouts of the 2-D r2c pipeline (see DESIGN.md "Data layout in HBM").
+//
+//   V  : the caller's slab, row-major, nxl rows x (ny+2) doubles == nxl x cy complex (cy = ny/2+1)
+//        -- byte-identical to hpxfft::util::vector_2d (core/include/hpxfft/util/vector_2d.hpp:198-213).
+//   I  : intermediate between the row pass and the column pass, *column-tiled*:
+//        I_q[r][ct][j][c]  r = source rank, ct = tile of CW adjacent ky owned by rank q,
+//        j = local row of rank r, c = column inside the tile.  Every (r, ct) block is one contiguous
+//        run of nxl*CW complex, so (i) the row kernel writes CW*16-byte segments, (ii) the exchange
+//        r -> q is ONE contiguous message, and (iii) the column kernel reads aligned CW*16-byte
+//        segments with no transpose anywhere.  This replaces split_vec + communicate + transpose_y_to_x
+//        of the reference (core/src/distributed/loop.cpp:19-27, 39-84, 87-106) and, for one rank,
+//        transpose_shared_y_to_x (core/src/shared/loop.cpp:18-25).
+//   S  : scratch between the two levels of a long column FFT, S[ct][k1][x2][c].
+#pragma once
+#include "fft_device.cuh"
+
+namespace hpxfft_b200 {
+
+constexpr int CW = 16;   // columns per tile: 16 complex = 256-byte segments
+constexpr int MAXP = 16; // max ranks
+
+// Destination of the row pass: column k of local row j.
+struct RowDst {
+    cd *base[MAXP];             // per destination rank q: start of the [ct][j][c] block written by this rank
+    unsigned long long tile_stride; // nxl * CW
+    unsigned cy;                // ny/2 + 1
+    unsigned wq0;               // columns owned by every rank but the last: cy / P
+    unsigned P;
+};
+
+__device__ __forceinline__ cd *rowdst_ptr(const RowDst &d, unsigned j, unsigned k)
+{
+    unsigned q = 0, kl = k;
+    if (d.P > 1) {
+        q = k / d.wq0;
+        if (q >= d.P) q = d.P - 1;
+        kl = k - q * d.wq0;
+    }
+    return d.base[q] + (unsigned long long) (kl / CW) * d.tile_stride + (unsigned long long) j * CW + (kl % CW);
+}
+
+// The column pass's view of I on the owning rank.
+struct InterView {
+    const cd *base;
+    unsigned long long rank_stride; // ntiles * nxl * CW
+    unsigned long long tile_stride; // nxl * CW
+    unsigned nxl;
+};
+
+__device__ __forceinline__ const cd *inter_ptr(const InterView &v, unsigned x, unsigned ct, unsigned c)
+{
+    const unsigned r = x / v.nxl, j = x - r * v.nxl;
+    return v.base + (unsigned long long) r * v.rank_stride + (unsigned long long) ct * v.tile_stride +
+           (unsigned long long) j * CW + c;
+}
+
+// Destination of the column pass: local column kl (< w) of global row kx.
+struct ColDst {
+    cd *base[MAXP];         // per destination rank r (owner of row kx)
+    unsigned pitch[MAXP];   // complex elements per destination row
+    unsigned col0[MAXP];    // first destination column
+    unsigned nxl;           // rows per rank
+    unsigned w;             // valid local columns on this rank
+};
+
+__device__ __forceinline__ cd *coldst_ptr(const ColDst &d, unsigned kx, unsigned kl)
+{
+    const unsigned r = kx / d.nxl, j = kx - r * d.nxl;
+    return d.base[r] + (unsigned long long) j * d.pitch[r] + d.col0[r] + kl;
+}
+
+}  // namespace hpxfft_b200
