@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the HPX-FFT 2-D r2c hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on the host cores
+
+A "step" is one 2-D r2c transform of one synthetic array.
+  N = 1 : BASELINE.json configs[1]  16384 x 16384 FP64 through the shared::loop path.
+  N > 1 : BASELINE.json configs[2]  32768 x 32768 FP64 slab-decomposed, distributed::loop all_to_all
+          (strong scaling over N = 2, 4, 8; falls back to 16384^2 if the size is unsupported).
+metric  = GFLOP/s with the BASELINE flop convention 2.5 * N * log2(N), N = nx * ny;  ms_per_step beside it.
+value   = device-resident throughput: K transforms enqueued back to back, CUDA events on the plan's
+          own stream, barrier + synchronize on both sides, max over ranks.
+e2e     = the same metric through the reference-facing call with HOST buffers: every step copies the
+          slab host->device from pinned memory, transforms, copies the result back (hpxfft_b200_transform).
+roofline= dominant kernel: algorithmic bytes per launch / its average CUDA-event duration over the
+          same timed region, against MEASURED_PEAKS.json hbm_gbs.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def flops(nx: int, ny: int) -> float:
+    n = float(nx) * float(ny)
+    return 2.5 * n * math.log2(n)
+
+
+def algorithmic_bytes(nx: int, ny: int) -> dict:
+    """one read + one write per dimension pass.  Per kernel:
+    rows  : read 8*nx*ny (reals)        + write 16*nx*cy
+    cols  : read 16*nx*cy               + write 16*nx*cy   (whole column pass, however many launches)"""
+    cy = ny // 2 + 1
+    return {"rows": 8.0 * nx * ny + 16.0 * nx * cy, "cols": 32.0 * nx * cy, "total": 8.0 * nx * ny + 48.0 * nx * cy}
+
+
+def measured_peaks() -> tuple[float, str]:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.gpu, self.proc, self.lines, self.thr = gpu_index, None, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus: int):
+    """torchrun env -> (rank, world, local_rank, dist or None).  gloo group for the bootstrap bytes
+    and the max-over-ranks reduction; the data path is NCCL / peer stores inside the library."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world == 1:
+        return 0, 1, 0, None
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    return rank, world, local, dist
+
+
+def run_ours(args) -> dict | None:
+    rank, world, local, dist = dist_setup(args.gpus)
+    import numpy as np
+    import torch
+    pkg = entry.load_package()
+    lib = pkg.capi.load()
+    if lib.hpxfft_b200_device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device; hpxfft_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+
+    if args.nx and args.ny:
+        nx, ny = args.nx, args.ny
+    elif world == 1:
+        nx = ny = 16384
+    else:
+        nx = ny = 32768
+    comm = None if world == 1 else args.run
+    nxl = nx // world
+    boot = pkg.distributed.Bootstrap()
+
+    def make_plan(nx_, ny_):
+        plan = C.c_void_p()
+        uid = None
+        if world > 1:
+            raw = None
+            if rank == 0:
+                buf = C.create_string_buffer(pkg.capi.UNIQUE_ID_BYTES)
+                pkg.capi.check(lib.hpxfft_b200_get_unique_id(buf))
+                raw = buf.raw
+            uid = boot.broadcast_bytes(raw, 0)
+        rc = lib.hpxfft_b200_create(C.byref(plan), nx_ // world, ny_ + 2, rank, world, local, comm.encode() if comm else None,
+                                    b"estimate", uid)
+        if rc != 0:
+            return None, lib.hpxfft_b200_last_error().decode()
+        if comm == "p2p" and world > 1:
+            cnt = lib.hpxfft_b200_ipc_count(plan)
+            buf = C.create_string_buffer(cnt * pkg.capi.IPC_HANDLE_BYTES)
+            pkg.capi.check(lib.hpxfft_b200_ipc_export(plan, buf))
+            pkg.capi.check(lib.hpxfft_b200_ipc_import(plan, b"".join(boot.all_gather_bytes(buf.raw))))
+        return plan, ""
+
+    plan, err = make_plan(nx, ny)
+    note = None
+    if plan is None and world > 1 and not (args.nx and args.ny):
+        note = f"{nx}x{ny} unsupported ({err}); fell back to 16384x16384"
+        nx = ny = 16384
+        nxl = nx // world
+        plan, err = make_plan(nx, ny)
+    if plan is None:
+        raise RuntimeError(err)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    stream = torch.cuda.ExternalStream(lib.hpxfft_b200_stream(plan), device=local)
+    pkg.capi.check(lib.hpxfft_b200_fill(plan, pkg.capi.PATTERN_UNIFORM, 42))
+
+    # ---- device-resident timing ------------------------------------------------------------
+    for _ in range(args.warmup):
+        pkg.capi.check(lib.hpxfft_b200_execute_async(plan))
+    pkg.capi.check(lib.hpxfft_b200_synchronize(plan))
+    pkg.capi.check(lib.hpxfft_b200_fill(plan, pkg.capi.PATTERN_UNIFORM, 42))  # keep magnitudes finite
+    pkg.capi.check(lib.hpxfft_b200_reset_timers(plan))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        pkg.capi.check(lib.hpxfft_b200_execute_async(plan))
+    e1.record(stream)
+    pkg.capi.check(lib.hpxfft_b200_synchronize(plan))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    meas = {k: lib.hpxfft_b200_measurement(plan, k.encode()) for k in
+            ("total", "first_fftw", "first_comm", "second_fftw", "second_comm", "second_trans", "rows_kernel",
+             "cols_levelA_kernel", "cols_levelB_kernel", "cols_kernel", "timer_samples")}
+    launches = lib.hpxfft_b200_launches_per_execute(plan) * args.steps
+
+    # ---- end to end: host buffers through the reference-facing call -----------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    host = pkg.vector_2d(nxl, ny + 2, 0.0, pinned=True)
+    host.data()[:, :ny] = np.random.default_rng(1234 + rank).uniform(-1, 1, (nxl, ny))
+    pkg.capi.check(lib.hpxfft_b200_transform(plan, host.data().ctypes.data))  # warm-up (page-touch, clocks)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pkg.capi.check(lib.hpxfft_b200_transform(plan, host.data().ctypes.data))
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    slab_bytes = nxl * (ny + 2) * 8
+
+    # ---- reductions: max over ranks -----------------------------------------------------------------
+    ms_step = ms_total / args.steps
+    if dist is not None:
+        t = torch.tensor([ms_step, e2e_ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms = float(t[0]), float(t[1])
+        km = torch.tensor([meas[k] for k in sorted(meas)], dtype=torch.float64)
+        dist.all_reduce(km, op=dist.ReduceOp.MAX)
+        meas = dict(zip(sorted(meas), [float(x) for x in km]))
+
+    result = None
+    if rank == 0:
+        gf = flops(nx, ny)
+        ab = algorithmic_bytes(nx, ny)
+        peak, how = measured_peaks()
+        kernels = {"rows_r2c": (meas["rows_kernel"], ab["rows"] / world),
+                   "cols_c2c": (meas["cols_kernel"], ab["cols"] / world)}
+        dom = max(kernels, key=lambda k: kernels[k][0])
+        dsec, dbytes = kernels[dom]
+        achieved = dbytes / dsec / 1e9 if dsec > 0 else 0.0
+        compute_sec = meas["rows_kernel"] + meas["cols_kernel"]
+        result = {
+            "metric": "2D r2c FFT GFLOP/s (2.5*N*log2N)", "value": gf / (ms_step * 1e-3) / 1e9, "unit": "GFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{nx}x{ny} FP64 r2c 2-D FFT, " + ("shared::loop path, 1 GPU" if world == 1 else
+                       f"distributed::loop {comm}, {world} GPUs, slab {nxl}x{ny + 2}"),
+                       "nx": nx, "ny": ny, "run": comm or "par", "plan": "estimate", "input": "uniform(-1,1) splitmix64 seed 42, generated on device",
+                       "l2_hygiene": f"inputs larger than L2 ({slab_bytes / 2**20:.0f} MiB slab per GPU vs 126 MiB L2)"},
+            "e2e": {"value": gf / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "h2d_bytes_per_step": slab_bytes * world, "d2h_bytes_per_step": slab_bytes * world,
+                    "api": "hpxfft_b200_transform (pinned host vector_2d -> device -> host)"},
+            "gpu_launches": launches,
+            "phases_ms": {k: meas[k] * 1e3 for k in meas if k != "timer_samples"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({how})", "traffic": None,
+                         "algorithmic_bytes_per_launch": dbytes, "avg_kernel_ms": dsec * 1e3,
+                         "whole_transform": {"algorithmic_bytes": ab["total"] / world, "compute_ms": compute_sec * 1e3,
+                                             "achieved": ab["total"] / world / compute_sec / 1e9 if compute_sec > 0 else 0.0,
+                                             "frac": ab["total"] / world / compute_sec / 1e9 / peak if compute_sec > 0 else 0.0}},
+            "clocks": clocks,
+        }
+        if note:
+            result["config"]["note"] = note
+        if world == 1 and not args.no_cpu_baseline:
+            result["cpu_baseline"] = cpu_baseline(nx, ny, budget_s=args.cpu_budget)
+    lib.hpxfft_b200_destroy(plan)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+def oracle_c_lib():
+    """The plain-C restatement (oracle/) -- executed here ONLY as the timed CPU baseline / reference arm."""
+    path = os.path.join(ROOT, "oracle", "libhpxfft_oracle.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    lib = C.CDLL(path)
+    lib.hpxfft_oracle_shared_loop.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
+    lib.hpxfft_oracle_shared_loop.restype = C.c_int
+    lib.hpxfft_oracle_max_threads.restype = C.c_int
+    return lib
+
+
+def cpu_sample_shape(nx: int, ny: int, cores: int) -> tuple[int, int]:
+    """Bounded sample of the workload: keep ny (row length), shrink nx until ~<= 2^26 points per 8 cores."""
+    budget_pts = (1 << 26) * max(1, cores // 8)
+    sx = nx
+    while sx * ny > budget_pts and sx > 256:
+        sx //= 2
+    return sx, ny
+
+
+def cpu_baseline(nx: int, ny: int, budget_s: float = 20.0) -> dict:
+    import numpy as np
+    lib = oracle_c_lib()
+    cores = min(lib.hpxfft_oracle_max_threads(), os.cpu_count() or 1)
+    sx, sy = cpu_sample_shape(nx, ny, cores)
+    a = np.zeros((sx, sy + 2))
+    a[:, :sy] = np.random.default_rng(0).uniform(-1, 1, (sx, sy))
+    best, spent, runs, tm = None, 0.0, 0, np.zeros(5)
+    while runs < 2 or (spent < budget_s and runs < 5):
+        v = a.copy()
+        assert lib.hpxfft_oracle_shared_loop(v.ctypes.data, sx, sy + 2, cores, tm.ctypes.data) == 0
+        spent += tm[0]
+        runs += 1
+        best = tm[0] if best is None else min(best, tm[0])
+    return {"value": flops(sx, sy) / best / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
+            "sample": f"{sx}x{sy} FP64 r2c (nx reduced from {nx}), best of {runs} runs of the 4-phase C restatement "
+                      f"(oracle/hpxfft_oracle.c, OpenMP); FFTW/HPX unavailable", "ms": best * 1e3}
+
+
+def run_reference(args) -> dict | None:
+    """Reference arm: the reference's own CPU algorithm (4-phase loop, core/src/shared/loop.cpp:56-113) on the
+    box's host cores.  HPX + FFTW cannot be built in this image, so the port in oracle/ is timed."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return None
+    import numpy as np
+    if args.nx and args.ny:
+        nx, ny = args.nx, args.ny
+    elif world == 1:
+        nx = ny = 16384
+    else:
+        nx = ny = 32768
+    lib = oracle_c_lib()
+    cores = min(lib.hpxfft_oracle_max_threads(), os.cpu_count() or 1)
+    sx, sy = cpu_sample_shape(nx, ny, cores)
+    a = np.zeros((sx, sy + 2))
+    a[:, :sy] = np.random.default_rng(0).uniform(-1, 1, (sx, sy))
+    tm = np.zeros(5)
+    times = []
+    for i in range(args.warmup + args.steps):
+        v = a.copy()
+        assert lib.hpxfft_oracle_shared_loop(v.ctypes.data, sx, sy + 2, cores, tm.ctypes.data) == 0
+        if i >= args.warmup:
+            times.append(tm[0])
+    ms = 1e3 * sum(times) / len(times)
+    val = flops(sx, sy) / (ms * 1e-3) / 1e9
+    sample = (f"{sx}x{sy} FP64 r2c per step (nx reduced from {nx} to bound the run); 4-phase C restatement of "
+              f"shared::loop (oracle/hpxfft_oracle.c, OpenMP {cores} threads); FFTW/HPX unavailable in this image")
+    comm = None if world == 1 else args.run
+    return {"impl": "reference", "metric": "2D r2c FFT GFLOP/s (2.5*N*log2N)", "value": val, "unit": "GFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{nx}x{ny} FP64 r2c 2-D FFT, " + ("shared::loop path" if world == 1 else f"distributed::loop {comm}"),
+                       "nx": nx, "ny": ny, "run": comm or "par", "plan": "estimate"},
+            "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=0)
+    ap.add_argument("--ny", type=int, default=0)
+    ap.add_argument("--run", default="all_to_all", choices=["all_to_all", "scatter", "p2p"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    res = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if res is not None:
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

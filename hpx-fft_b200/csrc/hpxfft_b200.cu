@@ -144,7 +144,12 @@ struct hpxfft_b200_plan {
     bool ipc_imported = false;
     // execution
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
+    // One event set per execute since the last reset (ring of EV_SETS): lets a benchmark launch K
+    // transforms back to back and still read per-phase / per-kernel averages afterwards.
+    static constexpr int EV_SETS = 64, EV_PER_SET = 7;
+    std::vector<cudaEvent_t> evs;   // EV_SETS * EV_PER_SET
+    cudaEvent_t ev_io[2] = {};      // upload / download timing
+    long nrec = 0;                  // executes enqueued since the last reset
     ncclComm_t comm = nullptr;
     int *d_barrier = nullptr;
     int launches = 0;
@@ -264,10 +269,11 @@ template <int N2> int launch_cols_B(const hpxfft_b200_plan *p, const cd *S, cons
     }
 
 int launch_cols(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles, cd *S, unsigned nx,
-                unsigned n1, unsigned n2, bool two_level, int *launches)
+                unsigned n1, unsigned n2, bool two_level, int *launches, cudaEvent_t mid = nullptr)
 {
     if (!two_level) {
         if (launches) *launches += 1;
+        if (mid) CU(cudaEventRecord(mid, p->stream));
         if (nx <= 256) { DISPATCH_POW2(launch_cols_single, nx, 1, p, in, out, ntiles) }
         return fail(HPXFFT_B200_EINVAL, "unsupported single-level column length %u", nx);
     }
@@ -278,6 +284,7 @@ int launch_cols(const hpxfft_b200_plan *p, const InterView &in, const ColDst &ou
             return fail(HPXFFT_B200_EINVAL, "unsupported level-A length %u", n1);
         };
         if (int rc = a()) return rc;
+        if (mid) CU(cudaEventRecord(mid, p->stream));
     }
     DISPATCH_POW2(launch_cols_B, n2, 16, p, S, out, n1, ntiles)
     return fail(HPXFFT_B200_EINVAL, "unsupported level-B length %u", n2);
@@ -439,11 +446,13 @@ int enqueue_transform(hpxfft_b200_plan *p)
     iv.tile_stride = (unsigned long long) p->nxl * CW;
     iv.rank_stride = (unsigned long long) p->ntiles * p->nxl * CW;
 
-    CU(cudaEventRecord(p->ev[0], p->stream));
+    cudaEvent_t *ev = p->evs.data() + (size_t) (p->nrec % hpxfft_b200_plan::EV_SETS) * hpxfft_b200_plan::EV_PER_SET;
+    p->nrec += 1;
+    CU(cudaEventRecord(ev[0], p->stream));
     // phase 1: r2c rows (+ fused split / transpose)           -> first_fftw (first_split, first_trans fused)
     if (int rc = launch_rows(p, rd, (unsigned) p->nxl, (const cd *) p->V, (unsigned) p->cy, p->m)) return rc;
     launches += 1;
-    CU(cudaEventRecord(p->ev[1], p->stream));
+    CU(cudaEventRecord(ev[1], p->stream));
     // phase 2: exchange #1                                    -> first_comm
     if (p->P > 1) {
         if (p->mode == MODE_P2P) {
@@ -451,10 +460,10 @@ int enqueue_transform(hpxfft_b200_plan *p)
         } else if (int rc = exchange1(p))
             return rc;
     }
-    CU(cudaEventRecord(p->ev[2], p->stream));
+    CU(cudaEventRecord(ev[2], p->stream));
     // phase 3: c2c columns (+ fused split / transpose)        -> second_fftw
-    if (int rc = launch_cols(p, iv, cdst, p->ntiles, p->S, (unsigned) p->nx, p->n1, p->n2, p->two_level, &launches)) return rc;
-    CU(cudaEventRecord(p->ev[3], p->stream));
+    if (int rc = launch_cols(p, iv, cdst, p->ntiles, p->S, (unsigned) p->nx, p->n1, p->n2, p->two_level, &launches, ev[6])) return rc;
+    CU(cudaEventRecord(ev[3], p->stream));
     // phase 4: exchange #2                                    -> second_comm
     if (p->P > 1) {
         if (p->mode == MODE_P2P) {
@@ -462,7 +471,7 @@ int enqueue_transform(hpxfft_b200_plan *p)
         } else if (int rc = exchange2(p))
             return rc;
     }
-    CU(cudaEventRecord(p->ev[4], p->stream));
+    CU(cudaEventRecord(ev[4], p->stream));
     // phase 5: unpack into the slab                           -> second_trans
     if (p->P > 1 && p->mode != MODE_P2P) {
         unpack_kernel<<<dim3((unsigned) p->nxl, (unsigned) p->P), 256, 0, p->stream>>>(p->bufB, (cd *) p->V, (unsigned) p->nxl,
@@ -470,28 +479,48 @@ int enqueue_transform(hpxfft_b200_plan *p)
         CU(cudaGetLastError());
         launches += 1;
     }
-    CU(cudaEventRecord(p->ev[5], p->stream));
+    CU(cudaEventRecord(ev[5], p->stream));
     p->launches = launches;
     return 0;
 }
 
 int read_timers(hpxfft_b200_plan *p)
 {
-    float ms[6] = {0};
-    for (int i = 0; i < 5; ++i) CU(cudaEventElapsedTime(&ms[i], p->ev[i], p->ev[i + 1]));
-    CU(cudaEventElapsedTime(&ms[5], p->ev[0], p->ev[5]));
+    // averages over the executes enqueued since the last reset (at most the EV_SETS most recent)
+    const long nset = p->nrec < hpxfft_b200_plan::EV_SETS ? p->nrec : hpxfft_b200_plan::EV_SETS;
+    if (nset <= 0) return 0;
+    double acc[8] = {0};
+    for (long sidx = 0; sidx < nset; ++sidx) {
+        const long slot = ((p->nrec - 1 - sidx) % hpxfft_b200_plan::EV_SETS + hpxfft_b200_plan::EV_SETS) % hpxfft_b200_plan::EV_SETS;
+        cudaEvent_t *ev = p->evs.data() + (size_t) slot * hpxfft_b200_plan::EV_PER_SET;
+        float ms = 0;
+        for (int i = 0; i < 5; ++i) {
+            CU(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            acc[i] += ms;
+        }
+        CU(cudaEventElapsedTime(&ms, ev[0], ev[5]));
+        acc[5] += ms;
+        CU(cudaEventElapsedTime(&ms, ev[2], ev[6]));
+        acc[6] += ms; // column level A (0 for single-level)
+        CU(cudaEventElapsedTime(&ms, ev[6], ev[3]));
+        acc[7] += ms; // column level B / single-level kernel
+    }
+    const double sc = 1e-3 / (double) nset;
     auto &m = p->meas;
-    m["total"] = ms[5] * 1e-3;
-    m["first_fftw"] = ms[0] * 1e-3;
+    m["total"] = acc[5] * sc;
+    m["first_fftw"] = acc[0] * sc;
     m["first_split"] = 0.0; // fused into the row kernel's store
-    m["first_comm"] = ms[1] * 1e-3;
+    m["first_comm"] = acc[1] * sc;
     m["first_trans"] = 0.0; // no transpose: the column kernel reads the tiled layout directly
-    m["second_fftw"] = ms[2] * 1e-3;
+    m["second_fftw"] = acc[2] * sc;
     m["second_split"] = 0.0;
-    m["second_comm"] = ms[3] * 1e-3;
-    m["second_trans"] = ms[4] * 1e-3;
-    m["rows_kernel"] = ms[0] * 1e-3;
-    m["cols_kernel"] = ms[2] * 1e-3;
+    m["second_comm"] = acc[3] * sc;
+    m["second_trans"] = acc[4] * sc;
+    m["rows_kernel"] = acc[0] * sc;
+    m["cols_kernel"] = acc[2] * sc;
+    m["cols_levelA_kernel"] = acc[6] * sc;
+    m["cols_levelB_kernel"] = acc[7] * sc;
+    m["timer_samples"] = (double) nset;
     return 0;
 }
 
@@ -556,7 +585,9 @@ void hpxfft_b200_destroy(hpxfft_b200_plan *p)
     cudaFree(p->tw_row);
     cudaFree(p->tw_col);
     cudaFree(p->d_barrier);
-    for (auto &e : p->ev)
+    for (auto &e : p->evs)
+        if (e) cudaEventDestroy(e);
+    for (auto &e : p->ev_io)
         if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -626,7 +657,10 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     CU(cudaEventCreate(&t0));
     CU(cudaEventCreate(&t1));
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(HPXFFT_B200_ECUDA, "stream create failed"));
-    for (auto &e : p->ev)
+    p->evs.assign((size_t) hpxfft_b200_plan::EV_SETS * hpxfft_b200_plan::EV_PER_SET, nullptr);
+    for (auto &e : p->evs)
+        if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(HPXFFT_B200_ECUDA, "event create failed"));
+    for (auto &e : p->ev_io)
         if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(HPXFFT_B200_ECUDA, "event create failed"));
     cudaEventRecord(t0, p->stream);
 
@@ -743,7 +777,7 @@ int hpxfft_b200_upload(hpxfft_b200_plan *p, const double *host_slab)
 {
     if (!p || !host_slab) return fail(HPXFFT_B200_EINVAL, "NULL argument");
     CU(cudaSetDevice(p->device));
-    cudaEvent_t a = p->ev[6], b = p->ev[7];
+    cudaEvent_t a = p->ev_io[0], b = p->ev_io[1];
     CU(cudaEventRecord(a, p->stream));
     CU(cudaMemcpyAsync(p->V, host_slab, p->nxl * p->n_col * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     CU(cudaEventRecord(b, p->stream));
@@ -758,7 +792,7 @@ int hpxfft_b200_download(hpxfft_b200_plan *p, double *host_slab)
 {
     if (!p || !host_slab) return fail(HPXFFT_B200_EINVAL, "NULL argument");
     CU(cudaSetDevice(p->device));
-    cudaEvent_t a = p->ev[6], b = p->ev[7];
+    cudaEvent_t a = p->ev_io[0], b = p->ev_io[1];
     CU(cudaEventRecord(a, p->stream));
     CU(cudaMemcpyAsync(host_slab, p->V, p->nxl * p->n_col * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaEventRecord(b, p->stream));
@@ -793,11 +827,22 @@ int hpxfft_b200_synchronize(hpxfft_b200_plan *p)
     if (!p) return fail(HPXFFT_B200_EINVAL, "NULL plan");
     CU(cudaSetDevice(p->device));
     CU(cudaStreamSynchronize(p->stream));
+    return read_timers(p);
+}
+
+int hpxfft_b200_reset_timers(hpxfft_b200_plan *p)
+{
+    if (!p) return fail(HPXFFT_B200_EINVAL, "NULL plan");
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->stream));
+    p->nrec = 0;
     return 0;
 }
 
 int hpxfft_b200_execute(hpxfft_b200_plan *p)
 {
+    if (!p) return fail(HPXFFT_B200_EINVAL, "NULL plan");
+    p->nrec = 0;
     if (int rc = hpxfft_b200_execute_async(p)) return rc;
     CU(cudaStreamSynchronize(p->stream));
     return read_timers(p);
@@ -808,6 +853,7 @@ int hpxfft_b200_transform(hpxfft_b200_plan *p, double *host_slab_inout)
     if (!p || !host_slab_inout) return fail(HPXFFT_B200_EINVAL, "NULL argument");
     CU(cudaSetDevice(p->device));
     const size_t bytes = p->nxl * p->n_col * sizeof(double);
+    p->nrec = 0;
     CU(cudaMemcpyAsync(p->V, host_slab_inout, bytes, cudaMemcpyHostToDevice, p->stream));
     if (int rc = enqueue_transform(p)) return rc;
     CU(cudaMemcpyAsync(host_slab_inout, p->V, bytes, cudaMemcpyDeviceToHost, p->stream));

@@ -102,16 +102,19 @@ int hpxfft_b200_fill(hpxfft_b200_plan *, int pattern, uint64_t seed);
  * asynchronous launch + stream synchronise; records the reference's timer keys from CUDA events.
  * Collective across ranks when nranks > 1. */
 int hpxfft_b200_execute(hpxfft_b200_plan *);
-/* same without the final synchronise / timer read-back (for back-to-back benchmarking) */
+/* Back-to-back operation: execute_async only enqueues; synchronize waits and sets every
+ * measurement key to the AVERAGE over the transforms enqueued since the last reset_timers / execute
+ * (at most the 64 most recent; key "timer_samples" says how many). */
 int hpxfft_b200_execute_async(hpxfft_b200_plan *);
 int hpxfft_b200_synchronize(hpxfft_b200_plan *);
+int hpxfft_b200_reset_timers(hpxfft_b200_plan *);
 /* upload + execute + download in one call: what initialize()+fft_2d_r2c() cost end to end */
 int hpxfft_b200_transform(hpxfft_b200_plan *, double *host_slab_inout);
 
 /* Replaces loop::get_measurement (core/src/shared/loop.cpp:192, distributed/loop.cpp:350): seconds;
  * keys total, first_fftw, first_trans, second_fftw, second_trans, plan, plan_flops (+ first_split,
  * first_comm, second_split, second_comm for distributed; extensions h2d, d2h, rows_kernel,
- * cols_kernel).  Unknown key -> 0.0 like std::map::operator[]. */
+ * cols_kernel, cols_levelA_kernel, cols_levelB_kernel, timer_samples).  Unknown key -> 0.0 like std::map::operator[]. */
 double hpxfft_b200_measurement(const hpxfft_b200_plan *, const char *key);
 
 /* Replaces loop::write_plans_to_file (core/src/shared/loop.cpp:194-212): appends a text description

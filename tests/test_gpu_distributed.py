@@ -1,0 +1,78 @@
+"""Multi-GPU parity: gathered distributed::loop result == shared::loop / oracle result of the gathered
+input, natural order, all ny/2+1 columns, for scatter / all_to_all / p2p.
+One process per GPU (spawned here), gloo for the bootstrap bytes, NCCL / peer stores for the data."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import gpu_count
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+CASES = [(64, 64), (16, 256), (256, 512), (1024, 2048), (2048, 64)]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pkg = entry.load_package()
+        oracle = entry.load_oracle()
+        results = []
+        cases = CASES + [(world, 32)]                       # n_x_local == 1
+        for (nx, ny) in cases:
+            nxl = nx // world
+            full = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=11)   # x-dependent input
+            ref = oracle.fft_2d_r2c_shared(full, workers=2)
+            for comm in ("all_to_all", "scatter", "p2p"):
+                slab = full[rank * nxl:(rank + 1) * nxl].copy()
+                fft = pkg.distributed.loop(device=rank)
+                fft.initialize(pkg.vector_2d.from_array(slab), comm, "estimate")
+                out = fft.fft_2d_r2c().data()
+                err = oracle.rel_l2(out, ref[rank * nxl:(rank + 1) * nxl])
+                # relative to the whole array's norm so that near-empty slabs do not inflate the figure
+                scale = np.linalg.norm(ref[rank * nxl:(rank + 1) * nxl]) / (np.linalg.norm(ref) / np.sqrt(world))
+                results.append((nx, ny, comm, err * scale, fft.get_measurement("total")))
+                del fft
+                dist.barrier()
+        q.put((rank, results))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "ERR " + repr(e) + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.timeout(900)
+def test_distributed_equals_shared(world):
+    if gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=800) for _ in procs)
+    for p in procs:
+        p.join(60)
+    for rank, rr in res.items():
+        assert not isinstance(rr, str), f"rank {rank}: {rr}"
+        for (nx, ny, comm, err, total) in rr:
+            assert err <= TOL, (rank, nx, ny, comm, err)
+            assert total >= 0.0

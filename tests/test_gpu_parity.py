@@ -1,0 +1,197 @@
+"""Parity of the CUDA path (through the C ABI / the loop classes) against the oracle.  Needs a GPU.
+
+Tolerances: the golden 4x4 case is exact (`==`, test/src/test_shared_loop.cpp:53); everything else is
+relative L2 error <= 1e-12 over all nx*(ny/2+1) complex outputs (BASELINE.json north_star), measured
+against the FP64 pocketfft restatement (itself ~2e-16 from the long-double oracle)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def shared_fft(pkg, a, method="fft_2d_r2c_par"):
+    fft = pkg.shared.loop(device=0)
+    fft.initialize(pkg.vector_2d.from_array(a.copy()), "estimate")
+    out = getattr(fft, method)()
+    return out.data(), fft
+
+
+# ---------------------------------------------------------------- golden vector (reference's own test)
+@pytest.mark.parametrize("method", ["fft_2d_r2c_par", "fft_2d_r2c_seq", "fft_2d_r2c"])
+def test_golden_shared_loop(pkg, oracle, method):
+    out, fft = shared_fft(pkg, oracle.GOLDEN_4x4_IN, method)
+    assert np.array_equal(out, oracle.GOLDEN_4x4_OUT)          # REQUIRE(out2 == expected_output)
+    assert fft.get_measurement("total") >= 0.0                  # REQUIRE(total >= 0.0)
+    assert fft.get_measurement("plan_flops") > 0.0
+    assert fft.get_measurement("no_such_key") == 0.0
+
+
+@pytest.mark.parametrize("comm", ["scatter", "all_to_all", "p2p"])
+def test_golden_distributed_loop_one_locality(pkg, oracle, comm):
+    # test/src/test_distributed_loop.cpp:17-48 with num_localities == 1
+    fft = pkg.distributed.loop(device=0)
+    fft.initialize(pkg.vector_2d.from_array(oracle.GOLDEN_4x4_IN.copy()), comm, "estimate")
+    out = fft.fft_2d_r2c()
+    assert np.array_equal(out.data(), oracle.GOLDEN_4x4_OUT)
+    assert fft.get_measurement("total") >= 0.0
+
+
+def test_golden_distributed_agas(pkg, oracle):
+    # test/src/test_distributed_agas.cpp:17-48 (plan flag "measure")
+    fft = pkg.distributed.agas(device=0)
+    fft.initialize(pkg.vector_2d.from_array(oracle.GOLDEN_4x4_IN.copy()), "scatter", "measure").result()
+    out = fft.fft_2d_r2c().result()
+    assert np.array_equal(out.data(), oracle.GOLDEN_4x4_OUT)
+
+
+# ---------------------------------------------------------------- 1-D kernels (the fftw_adapter seam)
+@pytest.mark.parametrize("ny", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_r2c_rows(pkg, lib, oracle, ny):
+    batch = 37 if ny < 8192 else 5
+    rng = np.random.default_rng(ny)
+    a = np.zeros((batch, ny + 2))
+    a[:, :ny] = rng.uniform(-1, 1, (batch, ny))
+    got = a.copy()
+    pkg.capi.check(lib.hpxfft_b200_r2c_rows(got.ctypes.data, batch, ny + 2, 0))
+    import scipy.fft as sfft
+    ref = sfft.rfft(a[:, :ny].astype(np.longdouble), axis=1)
+    assert oracle.rel_l2(got, np.ascontiguousarray(ref).view(np.longdouble).reshape(batch, -1)) <= 1e-13
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072])
+def test_c2c_cols(pkg, lib, oracle, n):
+    width = 19 if n <= 16384 else 3          # ragged: one full 16-column tile + a partial one
+    rng = np.random.default_rng(n)
+    a = rng.uniform(-1, 1, (n, width)) + 1j * rng.uniform(-1, 1, (n, width))
+    got = np.ascontiguousarray(a)
+    pkg.capi.check(lib.hpxfft_b200_c2c_cols(got.ctypes.data, n, width, 0))
+    import scipy.fft as sfft
+    ref = sfft.fft(a.astype(np.clongdouble), axis=0)
+    assert oracle.rel_l2(got.view(np.float64), np.ascontiguousarray(ref).view(np.longdouble)) <= 1e-13
+
+
+# ---------------------------------------------------------------- 2-D sweeps
+SWEEP = [(2, 2), (2, 4), (4, 2), (8, 8), (16, 64), (64, 16), (1, 32), (32, 2), (128, 128), (256, 512), (512, 256),
+         (1024, 64), (64, 2048), (512, 512), (2048, 1024), (1024, 4096)]
+
+
+@pytest.mark.parametrize("nx,ny", SWEEP)
+def test_small_pow2_sweep(pkg, oracle, nx, ny):
+    a = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=42)
+    got, _ = shared_fft(pkg, a)
+    ref = oracle.fft_2d_r2c_longdouble(a) if nx * ny <= 1 << 18 else oracle.fft_2d_r2c_shared(a, workers=4)
+    assert oracle.rel_l2(got, ref) <= TOL
+
+
+def test_x_dependence_is_real(pkg, oracle):
+    # the reference's tests only ever feed x-constant rows; a delta in x must produce the right phase ramp
+    nx, ny = 64, 32
+    a = np.zeros((nx, ny + 2))
+    a[5, 3] = 1.0
+    got, _ = shared_fft(pkg, a)
+    kx = np.arange(nx)[:, None]
+    ky = np.arange(ny // 2 + 1)[None, :]
+    ref = np.exp(-2j * np.pi * (5 * kx / nx + 3 * ky / ny))
+    assert np.abs(oracle.to_complex(got) - ref).max() < 1e-13
+
+
+@pytest.mark.parametrize("pattern", ["ramp", "uniform", "separable"])
+def test_c1_anchor_256x16384(pkg, oracle, oracle_c, pattern):
+    # BASELINE config 1: hpxfft_shared_loop --nx=256 --ny=16384
+    nx, ny = 256, 16384
+    pat = {"ramp": oracle.PATTERN_RAMP, "uniform": oracle.PATTERN_UNIFORM, "separable": oracle.PATTERN_SEPARABLE}[pattern]
+    a = oracle.make_input(nx, ny, pat, seed=42)
+    got, fft = shared_fft(pkg, a)
+    ref = a.copy()
+    assert oracle_c.hpxfft_oracle_shared_loop(ref.ctypes.data, nx, ny + 2, 0, None) == 0
+    assert oracle.rel_l2(got, ref) <= TOL
+    if pattern == "ramp":
+        assert oracle.rel_l2(got, oracle.ramp_analytic(nx, ny)) <= TOL
+    if pattern == "separable":
+        s = oracle.separable_spectrum(nx, ny, 42)
+        assert oracle.rel_l2(oracle.to_complex(got).real, s.real) <= TOL
+        assert oracle.rel_l2(oracle.to_complex(got).imag, s.imag) <= TOL
+    for key in ("total", "first_fftw", "second_fftw"):
+        assert fft.get_measurement(key) > 0.0
+
+
+def test_fill_matches_host_generator(pkg, lib, oracle):
+    nx, ny = 64, 256
+    for pat in (oracle.PATTERN_RAMP, oracle.PATTERN_UNIFORM, oracle.PATTERN_SEPARABLE):
+        plan = C.c_void_p()
+        pkg.capi.check(lib.hpxfft_b200_create(C.byref(plan), nx, ny + 2, 0, 1, 0, None, b"estimate", None))
+        pkg.capi.check(lib.hpxfft_b200_fill(plan, pat, 42))
+        got = np.empty((nx, ny + 2))
+        pkg.capi.check(lib.hpxfft_b200_download(plan, got.ctypes.data))
+        lib.hpxfft_b200_destroy(plan)
+        ref = oracle.make_input(nx, ny, pat, seed=42)
+        if pat == oracle.PATTERN_SEPARABLE:
+            assert np.abs(got - ref).max() < 1e-14
+        else:
+            assert np.array_equal(got, ref)
+
+
+def test_transform_end_to_end_and_plan_reuse(pkg, lib, oracle):
+    nx, ny = 128, 512
+    plan = C.c_void_p()
+    pkg.capi.check(lib.hpxfft_b200_create(C.byref(plan), nx, ny + 2, 0, 1, 0, None, b"estimate", None))
+    for seed in (1, 2, 3):   # the same plan object serves several transforms
+        a = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=seed)
+        got = a.copy()
+        pkg.capi.check(lib.hpxfft_b200_transform(plan, got.ctypes.data))
+        assert oracle.rel_l2(got, oracle.fft_2d_r2c_shared(a)) <= TOL
+    assert lib.hpxfft_b200_launches_per_execute(plan) == 3
+    lib.hpxfft_b200_destroy(plan)
+
+
+def test_write_plans_to_file(pkg, oracle, tmp_path):
+    _, fft = shared_fft(pkg, oracle.GOLDEN_4x4_IN)
+    path = tmp_path / "plans" / "plan.txt"
+    with pytest.raises(RuntimeError):                      # shared/loop.cpp:198-201
+        fft.write_plans_to_file(str(path))
+    path.parent.mkdir()
+    fft.write_plans_to_file(str(path))
+    text = path.read_text()
+    assert "FFTW r2c 1D plan:" in text and "FFTW c2c 1D plan:" in text
+
+
+# ---------------------------------------------------------------- full size (BASELINE config 2)
+def test_c2_16384_separable_and_properties(pkg, lib, oracle):
+    """16384 x 16384 on one GPU: input generated on the device, checked against the rank-4 separable
+    closed form (1-D long-double FFTs) on every output, plus size-independent properties."""
+    nx = ny = 16384
+    plan = C.c_void_p()
+    pkg.capi.check(lib.hpxfft_b200_create(C.byref(plan), nx, ny + 2, 0, 1, 0, None, b"estimate", None))
+    try:
+        pkg.capi.check(lib.hpxfft_b200_fill(plan, oracle.PATTERN_SEPARABLE, 42))
+        pkg.capi.check(lib.hpxfft_b200_execute(plan))
+        got = np.empty((nx, ny + 2))
+        pkg.capi.check(lib.hpxfft_b200_download(plan, got.ctypes.data))
+        z = oracle.to_complex(got)
+        a, b = oracle.sep_vectors(nx, ny, 42)
+        import scipy.fft as sfft
+        fa = sfft.fft(a.astype(np.longdouble), axis=1).astype(np.complex128)
+        fb = sfft.rfft(b.astype(np.longdouble), axis=1).astype(np.complex128)
+        num = den = 0.0
+        for r0 in range(0, nx, 1024):                       # blockwise to bound host memory
+            ref = np.einsum("rx,ry->xy", fa[:, r0:r0 + 1024], fb)
+            d = z[r0:r0 + 1024] - ref
+            num += float(np.vdot(d, d).real)
+            den += float(np.vdot(ref, ref).real)
+        assert (num / den) ** 0.5 <= TOL
+        # DC bin = sum of all inputs; Nyquist/DC columns of a real input have Hermitian symmetry in kx
+        assert abs(z[0, 0].imag) <= 1e-6 * abs(z[0, 0].real) + 1e-6
+        assert np.abs(z[1:, 0] - np.conj(z[:0:-1, 0])).max() <= 1e-9 * np.abs(z[:, 0]).max()
+        assert np.abs(z[1:, -1] - np.conj(z[:0:-1, -1])).max() <= 1e-9 * np.abs(z[:, -1]).max() + 1e-9
+        # ramp at full size against the closed form (the reference example's own input)
+        pkg.capi.check(lib.hpxfft_b200_fill(plan, oracle.PATTERN_RAMP, 0))
+        pkg.capi.check(lib.hpxfft_b200_execute(plan))
+        pkg.capi.check(lib.hpxfft_b200_download(plan, got.ctypes.data))
+        ref0 = oracle.ramp_analytic(1, ny)[0] * nx
+        assert oracle.rel_l2(got[0], ref0) <= TOL
+        assert np.abs(got[1:]).max() <= 1e-12 * np.abs(got[0]).max() * 16384
+    finally:
+        lib.hpxfft_b200_destroy(plan)
