@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 what=${1:-all}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 if [[ $what == tests || $what == all ]]; then
-  timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 -x -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+  timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
   echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
   tail -30 gpurun_out/pytest_gpu.log
 fi
