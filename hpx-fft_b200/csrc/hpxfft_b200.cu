@@ -136,7 +136,11 @@ struct hpxfft_b200_plan {
     double *V = nullptr;   // slab, nxl x n_col doubles
     cd *bufA = nullptr;    // send buffer of exchange #1 and #2 (nranks > 1, NCCL modes)
     cd *bufB = nullptr;    // I (intermediate / receive window of exchange #1); receive buffer of #2
-    cd *S = nullptr;       // four-step scratch
+    cd *zraw = nullptr;    // un-split row spectra, only for rows longer than 32768 reals
+    cd *S = nullptr;       // four-step scratch (full array, or an L2-resident ring of strips when fused)
+    bool fused = false;    // level A + level B in one persistent launch
+    unsigned lag = 0, nslot = 0, fused_grid = 0;
+    unsigned *ctl = nullptr; // tile counter + per-strip completion counters
     cd *tw_row = nullptr, *tw_col = nullptr;
     size_t bytesA = 0, bytesB = 0, bytesS = 0;
     // p2p
@@ -168,20 +172,27 @@ template <class K> int set_smem(K kernel, size_t bytes)
     return 0;
 }
 
-template <int M> int launch_rows_big(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+template <int M, int C = 1> int launch_rows_big(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
 {
     constexpr size_t smem = row_smem_bytes<M>();
     static int configured = -1;
     if (configured != p->device) {
-        if (int rc = set_smem(rows_r2c_kernel<M>, smem)) return rc;
+        if (int rc = set_smem(rows_r2c_kernel<M, C>, smem)) return rc;
         configured = p->device;
     }
     const unsigned ngroups = (nrows + row_group<M>() - 1) / row_group<M>();
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
-    const unsigned grid = ngroups < (unsigned) (4 * sms) ? ngroups : (unsigned) (4 * sms);
-    rows_r2c_kernel<M><<<grid, ROW_THREADS, smem, p->stream>>>(V, pitch, nrows, dst, p->tw_row);
+    const unsigned cap = (unsigned) (4 * sms) / C > 0 ? (unsigned) (4 * sms) / C : 1u;
+    const unsigned grid = ngroups < cap ? ngroups : cap;
+    if (C > 2 && !p->zraw) return fail(HPXFFT_B200_ESTATE, "long-row scratch missing");
+    rows_r2c_kernel<M, C><<<dim3(grid, C), ROW_THREADS, smem, p->stream>>>(V, pitch, nrows, dst, p->tw_row, p->zraw);
     CU(cudaGetLastError());
+    if (C > 2) {
+        const unsigned m = (unsigned) M * C;
+        herm_split_kernel<<<dim3((m / 2 + 1 + 255) / 256, nrows), 256, 0, p->stream>>>(p->zraw, m, nrows, dst, p->tw_row);
+        CU(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -210,7 +221,10 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
     case 2048: return launch_rows_big<2048>(p, dst, nrows, V, pitch);
     case 4096: return launch_rows_big<4096>(p, dst, nrows, V, pitch);
     case 8192: return launch_rows_big<8192>(p, dst, nrows, V, pitch);
-    default: return fail(HPXFFT_B200_EINVAL, "unsupported row length ny=%zu (ny/2 must be a power of two <= 8192)", 2 * m);
+    case 16384: return launch_rows_big<8192, 2>(p, dst, nrows, V, pitch);
+    case 32768: return launch_rows_big<8192, 4>(p, dst, nrows, V, pitch);
+    case 65536: return launch_rows_big<8192, 8>(p, dst, nrows, V, pitch);
+    default: return fail(HPXFFT_B200_EINVAL, "unsupported row length ny=%zu (ny/2 must be a power of two <= 65536)", 2 * m);
     }
 }
 
@@ -288,6 +302,53 @@ int launch_cols(const hpxfft_b200_plan *p, const InterView &in, const ColDst &ou
     }
     DISPATCH_POW2(launch_cols_B, n2, 16, p, S, out, n1, ntiles)
     return fail(HPXFFT_B200_EINVAL, "unsupported level-B length %u", n2);
+}
+
+template <int N1, int N2> int fused_occupancy(int *blocks_per_sm)
+{
+    constexpr size_t smem = fused_smem_bytes<N1, N2>();
+    if (int rc = set_smem(cols_fused_kernel<N1, N2>, smem)) return rc;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cols_fused_kernel<N1, N2>, fused_threads<N1, N2>(), smem));
+    return 0;
+}
+
+template <int N1, int N2>
+int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles)
+{
+    constexpr size_t smem = fused_smem_bytes<N1, N2>();
+    static int configured = -1;
+    if (configured != p->device) {
+        if (int rc = set_smem(cols_fused_kernel<N1, N2>, smem)) return rc;
+        configured = p->device;
+    }
+    CU(cudaMemsetAsync(p->ctl, 0, (1 + 2 * (size_t) ntiles) * sizeof(unsigned), p->stream));
+    FusedCtl ctl;
+    ctl.counter = p->ctl;
+    ctl.doneA = p->ctl + 1;
+    ctl.doneB = p->ctl + 1 + ntiles;
+    ctl.lag = p->lag;
+    ctl.nslot = p->nslot;
+    cols_fused_kernel<N1, N2><<<p->fused_grid, fused_threads<N1, N2>(), smem, p->stream>>>(in, p->S, out, p->tw_col, ntiles, ctl);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+#define FUSED_PAIRS(X) X(32, 16) X(32, 32) X(64, 32) X(64, 64) X(128, 64) X(128, 128) X(256, 128) X(256, 256) X(512, 256) X(512, 512)
+
+int launch_cols_fused(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles)
+{
+#define X(A, B) if (p->n1 == A && p->n2 == B) return launch_cols_fused_t<A, B>(p, in, out, ntiles);
+    FUSED_PAIRS(X)
+#undef X
+    return fail(HPXFFT_B200_EINVAL, "no fused column kernel for %u x %u", p->n1, p->n2);
+}
+
+int fused_blocks_per_sm(unsigned n1, unsigned n2, int *bps)
+{
+#define X(A, B) if (n1 == A && n2 == B) return fused_occupancy<A, B>(bps);
+    FUSED_PAIRS(X)
+#undef X
+    return fail(HPXFFT_B200_EINVAL, "no fused column kernel for %u x %u", n1, n2);
 }
 
 void choose_col_split(size_t nx, unsigned &n1, unsigned &n2, bool &two_level)
@@ -451,7 +512,7 @@ int enqueue_transform(hpxfft_b200_plan *p)
     CU(cudaEventRecord(ev[0], p->stream));
     // phase 1: r2c rows (+ fused split / transpose)           -> first_fftw (first_split, first_trans fused)
     if (int rc = launch_rows(p, rd, (unsigned) p->nxl, (const cd *) p->V, (unsigned) p->cy, p->m)) return rc;
-    launches += 1;
+    launches += 1 + (p->m > 16384 ? 1 : 0);
     CU(cudaEventRecord(ev[1], p->stream));
     // phase 2: exchange #1                                    -> first_comm
     if (p->P > 1) {
@@ -462,7 +523,12 @@ int enqueue_transform(hpxfft_b200_plan *p)
     }
     CU(cudaEventRecord(ev[2], p->stream));
     // phase 3: c2c columns (+ fused split / transpose)        -> second_fftw
-    if (int rc = launch_cols(p, iv, cdst, p->ntiles, p->S, (unsigned) p->nx, p->n1, p->n2, p->two_level, &launches, ev[6])) return rc;
+    if (p->fused) {
+        CU(cudaEventRecord(ev[6], p->stream));
+        if (int rc = launch_cols_fused(p, iv, cdst, p->ntiles)) return rc;
+        launches += 1;
+    } else if (int rc = launch_cols(p, iv, cdst, p->ntiles, p->S, (unsigned) p->nx, p->n1, p->n2, p->two_level, &launches, ev[6]))
+        return rc;
     CU(cudaEventRecord(ev[3], p->stream));
     // phase 4: exchange #2                                    -> second_comm
     if (p->P > 1) {
@@ -475,7 +541,7 @@ int enqueue_transform(hpxfft_b200_plan *p)
     // phase 5: unpack into the slab                           -> second_trans
     if (p->P > 1 && p->mode != MODE_P2P) {
         unpack_kernel<<<dim3((unsigned) p->nxl, (unsigned) p->P), 256, 0, p->stream>>>(p->bufB, (cd *) p->V, (unsigned) p->nxl,
-                                                                                      (unsigned) p->cy, p->wq0, (unsigned) p->P);
+                                                                                      (unsigned) p->cy, p->wq0, (unsigned) p->P, (unsigned) p->rank);
         CU(cudaGetLastError());
         launches += 1;
     }
@@ -582,6 +648,8 @@ void hpxfft_b200_destroy(hpxfft_b200_plan *p)
     cudaFree(p->bufA);
     cudaFree(p->bufB);
     cudaFree(p->S);
+    cudaFree(p->zraw);
+    cudaFree(p->ctl);
     cudaFree(p->tw_row);
     cudaFree(p->tw_col);
     cudaFree(p->d_barrier);
@@ -634,7 +702,7 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         hpxfft_b200_destroy(p);
         return rc;
     };
-    if (!is_pow2(p->m) || p->m > 8192) return bail(fail(HPXFFT_B200_EINVAL, "unsupported ny=%zu: ny/2 must be a power of two <= 8192", p->ny));
+    if (!is_pow2(p->m) || p->m > 65536) return bail(fail(HPXFFT_B200_EINVAL, "unsupported ny=%zu: ny/2 must be a power of two <= 65536", p->ny));
     if (!is_pow2(p->nx) || p->nx > (1u << 18)) return bail(fail(HPXFFT_B200_EINVAL, "unsupported nx=%zu: must be a power of two <= 2^18", p->nx));
     if (p->cy < (size_t) nranks) return bail(fail(HPXFFT_B200_EINVAL, "ny/2+1=%zu columns cannot be split over %d localities", p->cy, nranks));
 
@@ -669,6 +737,24 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     p->bytesB = (size_t) p->ntiles * p->nx * CW * sizeof(cd); // I: [r][ct][j][c], also >= nxl*cy for exchange #2
     if (p->bytesB < p->nxl * p->cy * sizeof(cd)) p->bytesB = p->nxl * p->cy * sizeof(cd);
     p->bytesS = p->two_level ? (size_t) p->ntiles * p->nx * CW * sizeof(cd) : 0;
+    if (p->two_level) {
+        const char *e = getenv("HPXFFT_B200_FUSED");
+        p->fused = !(e && e[0] == '0');
+    }
+    if (p->fused) {
+        int bps = 1, sms = 148;
+        if (int rc = fused_blocks_per_sm(p->n1, p->n2, &bps)) return bail(rc);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (const char *e = getenv("HPXFFT_B200_FUSED_BPS")) { int v = atoi(e); if (v >= 1 && v < bps) bps = v; }
+        p->fused_grid = (unsigned) (bps * sms);
+        const unsigned per_group = p->n1 + p->n2;
+        p->lag = (unsigned) ((3 * (size_t) p->fused_grid / 2 + per_group - 1) / per_group) + 1;
+        if (const char *e = getenv("HPXFFT_B200_LAG")) { int v = atoi(e); if (v >= 1) p->lag = (unsigned) v; }
+        p->nslot = 2 * p->lag + 1;
+        if (const char *e = getenv("HPXFFT_B200_NSLOT")) { int v = atoi(e); if (v > (int) p->lag) p->nslot = (unsigned) v; }
+        if (p->nslot > p->ntiles) p->nslot = p->ntiles > 0 ? p->ntiles : 1;
+        p->bytesS = (size_t) p->nslot * p->nx * CW * sizeof(cd);
+    }
     if (nranks > 1 && mode != MODE_P2P) {
         size_t tiles_all = 0;
         for (int q = 0; q < nranks; ++q) tiles_all += p->ntiles_of[q];
@@ -684,7 +770,9 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     } while (0)
     CUB(cudaMalloc(&p->V, bytesV));
     CUB(cudaMalloc(&p->bufB, p->bytesB));
+    if (p->m > 16384) CUB(cudaMalloc(&p->zraw, p->nxl * p->m * sizeof(cd)));
     if (p->bytesS) CUB(cudaMalloc(&p->S, p->bytesS));
+    if (p->fused) CUB(cudaMalloc(&p->ctl, (1 + 2 * (size_t) p->ntiles) * sizeof(unsigned)));
     if (p->bytesA) CUB(cudaMalloc(&p->bufA, p->bytesA));
     CUB(cudaMemsetAsync(p->V, 0, bytesV, p->stream));
     CUB(cudaMemsetAsync(p->bufB, 0, p->bytesB, p->stream));
@@ -730,8 +818,8 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
              p->ny, p->m, p->m <= 16 ? "register-resident" : "shared-memory pencil", p->m <= 16 ? (int) p->m : ROW_PT);
     p->row_desc = buf;
     if (p->two_level)
-        snprintf(buf, sizeof(buf), "c2c columns: n=%zu four-step %u x %u on %d-column tiles (level A strided + twiddle, level B contiguous)",
-                 p->nx, p->n1, p->n2, CW);
+        snprintf(buf, sizeof(buf), "c2c columns: n=%zu four-step %u x %u on %d-column tiles (level A strided + twiddle, level B contiguous)%s",
+                 p->nx, p->n1, p->n2, CW, p->fused ? ", fused persistent launch with L2-resident scratch ring" : "");
     else
         snprintf(buf, sizeof(buf), "c2c columns: n=%zu single Stockham tile FFT on %d-column tiles", p->nx, CW);
     p->col_desc = buf;
@@ -885,7 +973,7 @@ void *hpxfft_b200_stream(hpxfft_b200_plan *p) { return p ? (void *) p->stream : 
 int hpxfft_b200_launches_per_execute(const hpxfft_b200_plan *p)
 {
     if (!p) return 0;
-    int n = 1 + (p->two_level ? 2 : 1);
+    int n = 1 + ((p->two_level && !p->fused) ? 2 : 1) + (p->m > 16384 ? 1 : 0);
     if (p->P > 1 && p->mode != MODE_P2P) n += 1;
     return n;
 }
@@ -912,7 +1000,7 @@ int hpxfft_b200_r2c_rows(double *host_rows, size_t batch, size_t n_col, int devi
 {
     if (!host_rows || batch == 0 || n_col < 4 || (n_col & 1)) return fail(HPXFFT_B200_EINVAL, "bad arguments");
     const size_t cy = n_col / 2, ny = 2 * cy - 2, m = ny / 2;
-    if (!is_pow2(m) || m > 8192) return fail(HPXFFT_B200_EINVAL, "unsupported ny=%zu", ny);
+    if (!is_pow2(m) || m > 65536) return fail(HPXFFT_B200_EINVAL, "unsupported ny=%zu", ny);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -934,8 +1022,9 @@ int hpxfft_b200_r2c_rows(double *host_rows, size_t batch, size_t n_col, int devi
         cudaFree(p->V);
         cudaFree(p->bufB);
         cudaFree(p->tw_row);
+        cudaFree(p->zraw);
         if (p->stream) cudaStreamDestroy(p->stream);
-        p->V = nullptr; p->bufB = nullptr; p->tw_row = nullptr; p->stream = nullptr;
+        p->V = nullptr; p->bufB = nullptr; p->tw_row = nullptr; p->zraw = nullptr; p->stream = nullptr;
     };
 #define CUR(call)                                                                                        \
     do {                                                                                                 \
@@ -949,6 +1038,7 @@ int hpxfft_b200_r2c_rows(double *host_rows, size_t batch, size_t n_col, int devi
     CUR(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CUR(cudaMalloc(&p->V, bytes));
     CUR(cudaMalloc(&p->bufB, tbytes));
+    if (m > 16384) CUR(cudaMalloc(&p->zraw, batch * m * sizeof(cd)));
     CUR(cudaMalloc(&p->tw_row, t.size() * sizeof(double2)));
     CUR(cudaMemcpyAsync(p->tw_row, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
     CUR(cudaMemcpyAsync(p->V, host_rows, bytes, cudaMemcpyHostToDevice, p->stream));

@@ -46,9 +46,11 @@ __global__ void fill_kernel(double *__restrict__ V, unsigned nxl, unsigned ny, u
 // exchange#2 unpack: recv2 holds, for every source rank q, a dense [nxl][w_q] block; scatter it into
 // V[j][c_q + kl].  Replaces transpose_x_to_y (core/src/distributed/loop.cpp:108-127) in natural ky order.
 // grid = (nxl, P)
-__global__ void unpack_kernel(const cd *__restrict__ recv2, cd *__restrict__ V, unsigned nxl, unsigned cy, unsigned wq0, unsigned P)
+__global__ void unpack_kernel(const cd *__restrict__ recv2, cd *__restrict__ V, unsigned nxl, unsigned cy, unsigned wq0, unsigned P,
+                              unsigned me)
 {
     const unsigned j = blockIdx.x, q = blockIdx.y;
+    if (q == me) return; // this rank's own columns were written straight into V by the column kernel
     const unsigned c0 = q * wq0;
     const unsigned w = (q == P - 1) ? cy - c0 : wq0;
     const cd *src = recv2 + (unsigned long long) nxl * c0 + (unsigned long long) j * w;

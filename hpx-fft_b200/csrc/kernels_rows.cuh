@@ -48,9 +48,31 @@ __device__ __forceinline__ void herm_pair(cd a, cd b, cd w, cd &xk, cd &xmk)
     xmk = make_double2(e.x - t.y, -(e.y + t.x));
 }
 
+// Long rows (m = M*C > 8192 complex): decimation in frequency over the leading index.  CTA c of a row
+// computes y_c[j] = w_m^(j c) * sum_{j1<C} z[j + j1 M] w_C^(j1 c), whose M-point FFT is Z[c + C k2].
+// Every CTA reads the whole row (served by L2 for all but the first reader) and no CTA talks to another.
+template <int M, int C>
+__device__ __forceinline__ cd load_split(const cd *__restrict__ zrow, int idx, int c, const cd *__restrict__ tw)
+{
+    if constexpr (C == 1) {
+        return ld_stream(zrow + idx);
+    } else if constexpr (C == 2) {
+        const cd a = ld_stream(zrow + idx), b = ld_stream(zrow + idx + M);
+        if (c == 0) return cadd(a, b);
+        return cmul(csub(a, b), ldtw(tw, 2u * (unsigned) idx));
+    } else {
+        cd acc = ld_stream(zrow + idx);
+#pragma unroll
+        for (int j1 = 1; j1 < C; ++j1)
+            acc = cadd(acc, cmul(ld_stream(zrow + idx + j1 * M), ldtw(tw, (unsigned) ((j1 * c) % C) * (unsigned) (2 * M))));
+        return c == 0 ? acc : cmul(acc, ldtw(tw, 2u * (unsigned) idx * (unsigned) c));
+    }
+}
+
 // one prefix pass: radix R, NS = product of earlier radices
-template <int M, int R, int NS, bool FIRST>
-__device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__restrict__ zrow, const cd *__restrict__ tw, int lt)
+template <int M, int C, int R, int NS, bool FIRST>
+__device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__restrict__ zrow, const cd *__restrict__ tw, int lt,
+                                         int c)
 {
     constexpr int PS = RowPlan<M>::PS;
     constexpr int NB = ROW_PT / R, T = M / R, TPR = row_tpr<M>();
@@ -61,7 +83,7 @@ __device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__re
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (FIRST)
-                v[b * R + r] = ld_stream(zrow + j + r * T);
+                v[b * R + r] = load_split<M, C>(zrow, j + r * T, c, tw);
             else
                 v[b * R + r] = sm[rpad<PS>(j + r * T)];
         }
@@ -76,7 +98,7 @@ __device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__re
         for (int r = 0; r < R; ++r) w[r] = v[b * R + r];
         if (NS > 1) {
 #pragma unroll
-            for (int r = 1; r < R; ++r) w[r] = cmul(w[r], ldtw(tw, (unsigned) (r * k) * (unsigned) (2 * M / (NS * R))));
+            for (int r = 1; r < R; ++r) w[r] = cmul(w[r], ldtw(tw, (unsigned) (r * k) * (unsigned) (2 * C * M / (NS * R))));
         }
         fft_dif<R>(w);
         const int j0 = ((j - k) << LGR) + k;
@@ -86,16 +108,21 @@ __device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__re
     __syncthreads();
 }
 
-// tw: w_n^i, i < n = 2M.  V rows have `pitch` complex (= cy) elements.
-template <int M>
+// tw: w_n^i, i < n = 2*M*C.  V rows have `pitch` complex (= cy) elements.  grid = (row groups, C).
+// C <= 2: Hermitian split fused (the partner of Z[c + C k2] lives in the same CTA); output via RowDst.
+// C  > 2: the partner lives in CTA C-c, so the raw Z is written to `zraw` (row-major, pitch m = M*C) and
+//         herm_split_kernel finishes the job.
+template <int M, int C>
 __global__ void __launch_bounds__(ROW_THREADS, 1)
-    rows_r2c_kernel(const cd *__restrict__ V, unsigned pitch, unsigned nxl, RowDst dst, const cd *__restrict__ tw)
+    rows_r2c_kernel(const cd *__restrict__ V, unsigned pitch, unsigned nxl, RowDst dst, const cd *__restrict__ tw, cd *__restrict__ zraw)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using P = RowPlan<M>;
     constexpr int PS = P::PS, TPR = row_tpr<M>(), G = row_group<M>(), LP = row_lp<M>();
     constexpr int PP = M / 16; // columns of the last pass
+    constexpr unsigned MM = (unsigned) M * C; // complex length of the whole row
     const int g = threadIdx.x / TPR, lt = threadIdx.x % TPR;
+    const int c = C == 1 ? 0 : (int) blockIdx.y;
     cd *sm = reinterpret_cast<cd *>(smem_raw) + g * LP;
     const unsigned ngroups = (nxl + G - 1) / G;
 
@@ -104,11 +131,13 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
         const bool valid = row < nxl;
         const cd *zrow = V + (unsigned long long) (valid ? row : nxl - 1) * pitch;
         cd v[ROW_PT];
-        row_pass<M, P::R0, 1, true>(v, sm, zrow, tw, lt);
-        if constexpr (P::NPRE == 2) row_pass<M, P::R1, P::R0, false>(v, sm, zrow, tw, lt);
+        row_pass<M, C, P::R0, 1, true>(v, sm, zrow, tw, lt, c);
+        if constexpr (P::NPRE == 2) row_pass<M, C, P::R1, P::R0, false>(v, sm, zrow, tw, lt, c);
 
-        // ---- last pass: two radix-16 butterflies (columns jA, jB) + Hermitian split ----
-        const int jA = lt, jB = lt ? PP - lt : PP / 2;
+        // ---- last pass: two radix-16 butterflies (columns jA, jB) ----
+        // partner of k2 is M - k2 (c == 0) or M - 1 - k2 (C == 2, c == 1)
+        const bool odd = (C == 2 && c == 1);
+        const int jA = lt, jB = odd ? PP - 1 - lt : (lt ? PP - lt : PP / 2);
         cd A[16], B[16];
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
@@ -117,51 +146,82 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
         }
 #pragma unroll
         for (int r = 1; r < 16; ++r) {
-            A[r] = cmul(A[r], ldtw(tw, 2u * (unsigned) (r * jA)));
-            B[r] = cmul(B[r], ldtw(tw, 2u * (unsigned) (r * jB)));
+            A[r] = cmul(A[r], ldtw(tw, (unsigned) (2 * C) * (unsigned) (r * jA)));
+            B[r] = cmul(B[r], ldtw(tw, (unsigned) (2 * C) * (unsigned) (r * jB)));
         }
         fft_dif<16>(A);
         fft_dif<16>(B);
-        // natural order: Z[j + s*PP] = X_[bitrev(s)]
-        if (lt != 0) {
+        // natural order: Z[c + C*(j + s*PP)] = X_[bitrev(s)]
+        if constexpr (C > 2) {
+            if (valid) {
+                cd *zr = zraw + (unsigned long long) row * MM;
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    st_stream(zr + (unsigned) c + (unsigned) C * (unsigned) (jA + s * PP), A[bitrev(s, 4)]);
+                    st_stream(zr + (unsigned) c + (unsigned) C * (unsigned) (jB + s * PP), B[bitrev(s, 4)]);
+                }
+            }
+        } else if (odd || lt != 0) {
 #pragma unroll
             for (int s = 0; s < 16; ++s) {
-                const unsigned kA = (unsigned) (jA + s * PP);
+                const unsigned kA = (unsigned) c + (unsigned) C * (unsigned) (jA + s * PP);
                 cd xk, xmk;
                 herm_pair(A[bitrev(s, 4)], B[bitrev(15 - s, 4)], ldtw(tw, kA), xk, xmk);
                 if (valid) {
                     st_stream(rowdst_ptr(dst, row, kA), xk);
-                    st_stream(rowdst_ptr(dst, row, (unsigned) M - kA), xmk);
+                    st_stream(rowdst_ptr(dst, row, MM - kA), xmk);
                 }
             }
         } else {
             const cd z0 = A[0];
             if (valid) {
                 st_stream(rowdst_ptr(dst, row, 0u), make_double2(z0.x + z0.y, 0.0));
-                st_stream(rowdst_ptr(dst, row, (unsigned) M), make_double2(z0.x - z0.y, 0.0));
+                st_stream(rowdst_ptr(dst, row, MM), make_double2(z0.x - z0.y, 0.0));
             }
 #pragma unroll
             for (int s = 1; s < 8; ++s) {
-                const unsigned k = (unsigned) (s * PP);
+                const unsigned k = (unsigned) C * (unsigned) (s * PP);
                 cd xk, xmk;
                 herm_pair(A[bitrev(s, 4)], A[bitrev(16 - s, 4)], ldtw(tw, k), xk, xmk);
                 if (valid) {
                     st_stream(rowdst_ptr(dst, row, k), xk);
-                    st_stream(rowdst_ptr(dst, row, (unsigned) M - k), xmk);
+                    st_stream(rowdst_ptr(dst, row, MM - k), xmk);
                 }
             }
-            if (valid) st_stream(rowdst_ptr(dst, row, (unsigned) (8 * PP)), cconj(A[bitrev(8, 4)]));
+            if (valid) st_stream(rowdst_ptr(dst, row, (unsigned) C * (unsigned) (8 * PP)), cconj(A[bitrev(8, 4)]));
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
-                const unsigned k = (unsigned) (PP / 2 + s * PP);
+                const unsigned k = (unsigned) C * (unsigned) (PP / 2 + s * PP);
                 cd xk, xmk;
                 herm_pair(B[bitrev(s, 4)], B[bitrev(15 - s, 4)], ldtw(tw, k), xk, xmk);
                 if (valid) {
                     st_stream(rowdst_ptr(dst, row, k), xk);
-                    st_stream(rowdst_ptr(dst, row, (unsigned) M - k), xmk);
+                    st_stream(rowdst_ptr(dst, row, MM - k), xmk);
                 }
             }
         }
+    }
+}
+
+// Hermitian split as a separate pass (rows longer than 2*8192 complex): zraw[row][k], k < m  ->  X[k], k <= m.
+// grid = (ceil((m/2+1)/256), nxl)
+__global__ void herm_split_kernel(const cd *__restrict__ zraw, unsigned m, unsigned nxl, RowDst dst, const cd *__restrict__ tw)
+{
+    const unsigned row = blockIdx.y;
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nxl || k > m / 2) return;
+    const cd *zr = zraw + (unsigned long long) row * m;
+    if (k == 0) {
+        const cd z0 = zr[0];
+        *rowdst_ptr(dst, row, 0u) = make_double2(z0.x + z0.y, 0.0);
+        *rowdst_ptr(dst, row, m) = make_double2(z0.x - z0.y, 0.0);
+    } else if (2 * k == m) {
+        *rowdst_ptr(dst, row, k) = cconj(zr[k]);
+    } else {
+        cd xk, xmk;
+        herm_pair(zr[k], zr[m - k], ldtw(tw, k), xk, xmk);
+        *rowdst_ptr(dst, row, k) = xk;
+        *rowdst_ptr(dst, row, m - k) = xmk;
     }
 }
 

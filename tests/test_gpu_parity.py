@@ -48,7 +48,7 @@ def test_golden_distributed_agas(pkg, oracle):
 
 
 # ---------------------------------------------------------------- 1-D kernels (the fftw_adapter seam)
-@pytest.mark.parametrize("ny", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize("ny", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072])
 def test_r2c_rows(pkg, lib, oracle, ny):
     batch = 37 if ny < 8192 else 5
     rng = np.random.default_rng(ny)
@@ -75,7 +75,7 @@ def test_c2c_cols(pkg, lib, oracle, n):
 
 # ---------------------------------------------------------------- 2-D sweeps
 SWEEP = [(2, 2), (2, 4), (4, 2), (8, 8), (16, 64), (64, 16), (1, 32), (32, 2), (128, 128), (256, 512), (512, 256),
-         (1024, 64), (64, 2048), (512, 512), (2048, 1024), (1024, 4096)]
+         (1024, 64), (64, 2048), (512, 512), (2048, 1024), (1024, 4096), (64, 32768), (16, 65536), (8, 131072)]
 
 
 @pytest.mark.parametrize("nx,ny", SWEEP)
