@@ -360,7 +360,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=0)
     ap.add_argument("--ny", type=int, default=0)
-    ap.add_argument("--run", default="all_to_all", choices=["all_to_all", "scatter", "p2p"])
+    ap.add_argument("--comm", "--run", dest="run", default="all_to_all", choices=["all_to_all", "scatter", "p2p"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
