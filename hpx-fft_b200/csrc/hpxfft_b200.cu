@@ -121,6 +121,15 @@ void make_twiddles(std::vector<double2> &t, size_t n)
     }
 }
 
+// [x2][k1] = w_nx^(k1*x2), nx = n1*n2, from the length-nx table
+void make_interlevel(std::vector<double2> &w2, const std::vector<double2> &t, unsigned n1, unsigned n2)
+{
+    const size_t nx = (size_t) n1 * n2;
+    w2.resize(nx);
+    for (size_t x2 = 0; x2 < n2; ++x2)
+        for (size_t k1 = 0; k1 < n1; ++k1) w2[x2 * n1 + k1] = t[(k1 * x2) % nx];
+}
+
 }  // namespace
 
 struct hpxfft_b200_plan {
@@ -139,9 +148,11 @@ struct hpxfft_b200_plan {
     cd *zraw = nullptr;    // un-split row spectra, only for rows longer than 32768 reals
     cd *S = nullptr;       // four-step scratch (full array, or an L2-resident ring of strips when fused)
     bool fused = false;    // level A + level B in one persistent launch
+    bool fused_tma = false; // ... with the warp-specialised TMA-bulk / mbarrier pipeline
     unsigned lag = 0, nslot = 0, fused_grid = 0;
     unsigned *ctl = nullptr; // tile counter + per-strip completion counters
     cd *tw_row = nullptr, *tw_col = nullptr;
+    cd *tw_il = nullptr;   // inter-level twiddles of the four-step column FFT, [x2][k1] = w_nx^(k1*x2)
     size_t bytesA = 0, bytesB = 0, bytesS = 0;
     // p2p
     std::vector<void *> peerI, peerV;
@@ -158,7 +169,7 @@ struct hpxfft_b200_plan {
     int *d_barrier = nullptr;
     int launches = 0;
     std::map<std::string, double> meas;
-    std::string plan_flag, row_desc, col_desc;
+    std::string plan_flag, row_desc, col_desc, col_desc_extra;
 };
 
 namespace {
@@ -230,7 +241,7 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
 
 template <int N> int launch_cols_single(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles)
 {
-    constexpr size_t smem = col_smem_bytes(N);
+    constexpr size_t smem = single_smem_bytes<N>();
     static int configured = -1;
     if (configured != p->device) {
         if (int rc = set_smem(cols_single_kernel<N>, smem)) return rc;
@@ -243,20 +254,20 @@ template <int N> int launch_cols_single(const hpxfft_b200_plan *p, const InterVi
 
 template <int N1> int launch_cols_A(const hpxfft_b200_plan *p, const InterView &in, cd *S, unsigned n2, unsigned ntiles)
 {
-    constexpr size_t smem = col_smem_bytes(N1);
+    constexpr size_t smem = levelA_smem_bytes<N1>();
     static int configured = -1;
     if (configured != p->device) {
         if (int rc = set_smem(cols_levelA_kernel<N1>, smem)) return rc;
         configured = p->device;
     }
-    cols_levelA_kernel<N1><<<dim3(n2, ntiles), col_threads(N1), smem, p->stream>>>(in, S, n2, p->tw_col);
+    cols_levelA_kernel<N1><<<dim3(n2, ntiles), col_threads(N1), smem, p->stream>>>(in, S, n2, p->tw_col, p->tw_il);
     CU(cudaGetLastError());
     return 0;
 }
 
 template <int N2> int launch_cols_B(const hpxfft_b200_plan *p, const cd *S, const ColDst &out, unsigned n1, unsigned ntiles)
 {
-    constexpr size_t smem = col_smem_bytes(N2);
+    constexpr size_t smem = single_smem_bytes<N2>();
     static int configured = -1;
     if (configured != p->device) {
         if (int rc = set_smem(cols_levelB_kernel<N2>, smem)) return rc;
@@ -304,8 +315,14 @@ int launch_cols(const hpxfft_b200_plan *p, const InterView &in, const ColDst &ou
     return fail(HPXFFT_B200_EINVAL, "unsupported level-B length %u", n2);
 }
 
-template <int N1, int N2> int fused_occupancy(int *blocks_per_sm)
+template <int N1, int N2> int fused_occupancy(int *blocks_per_sm, bool tma)
 {
+    if (tma) {
+        constexpr size_t smem = tma_smem_bytes<N1, N2>();
+        if (int rc = set_smem(cols_fused_tma_kernel<N1, N2>, smem)) return rc;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cols_fused_tma_kernel<N1, N2>, tma_threads<N1, N2>(), smem));
+        return 0;
+    }
     constexpr size_t smem = fused_smem_bytes<N1, N2>();
     if (int rc = set_smem(cols_fused_kernel<N1, N2>, smem)) return rc;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cols_fused_kernel<N1, N2>, fused_threads<N1, N2>(), smem));
@@ -319,6 +336,7 @@ int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const Co
     static int configured = -1;
     if (configured != p->device) {
         if (int rc = set_smem(cols_fused_kernel<N1, N2>, smem)) return rc;
+        if (int rc = set_smem(cols_fused_tma_kernel<N1, N2>, tma_smem_bytes<N1, N2>())) return rc;
         configured = p->device;
     }
     CU(cudaMemsetAsync(p->ctl, 0, (1 + 2 * (size_t) ntiles) * sizeof(unsigned), p->stream));
@@ -328,7 +346,11 @@ int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const Co
     ctl.doneB = p->ctl + 1 + ntiles;
     ctl.lag = p->lag;
     ctl.nslot = p->nslot;
-    cols_fused_kernel<N1, N2><<<p->fused_grid, fused_threads<N1, N2>(), smem, p->stream>>>(in, p->S, out, p->tw_col, ntiles, ctl);
+    if (p->fused_tma)
+        cols_fused_tma_kernel<N1, N2><<<p->fused_grid, tma_threads<N1, N2>(), tma_smem_bytes<N1, N2>(), p->stream>>>(in, p->S, out, p->tw_col,
+                                                                                                          p->tw_il, ntiles, ctl);
+    else
+        cols_fused_kernel<N1, N2><<<p->fused_grid, fused_threads<N1, N2>(), smem, p->stream>>>(in, p->S, out, p->tw_col, p->tw_il, ntiles, ctl);
     CU(cudaGetLastError());
     return 0;
 }
@@ -343,9 +365,9 @@ int launch_cols_fused(const hpxfft_b200_plan *p, const InterView &in, const ColD
     return fail(HPXFFT_B200_EINVAL, "no fused column kernel for %u x %u", p->n1, p->n2);
 }
 
-int fused_blocks_per_sm(unsigned n1, unsigned n2, int *bps)
+int fused_blocks_per_sm(unsigned n1, unsigned n2, int *bps, bool tma)
 {
-#define X(A, B) if (n1 == A && n2 == B) return fused_occupancy<A, B>(bps);
+#define X(A, B) if (n1 == A && n2 == B) return fused_occupancy<A, B>(bps, tma);
     FUSED_PAIRS(X)
 #undef X
     return fail(HPXFFT_B200_EINVAL, "no fused column kernel for %u x %u", n1, n2);
@@ -652,6 +674,7 @@ void hpxfft_b200_destroy(hpxfft_b200_plan *p)
     cudaFree(p->ctl);
     cudaFree(p->tw_row);
     cudaFree(p->tw_col);
+    cudaFree(p->tw_il);
     cudaFree(p->d_barrier);
     for (auto &e : p->evs)
         if (e) cudaEventDestroy(e);
@@ -740,10 +763,13 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     if (p->two_level) {
         const char *e = getenv("HPXFFT_B200_FUSED");
         p->fused = !(e && e[0] == '0');
+        p->fused_tma = p->fused && (e && e[0] == '2'); // HPXFFT_B200_FUSED=2 selects the TMA-bulk/mbarrier variant
+        // N = 512 tiles need 2 x 128 KB with a staging buffer: fall back to the plain fused kernel
+        if (p->n1 > 256 || p->n2 > 256) p->fused_tma = false;
     }
     if (p->fused) {
         int bps = 1, sms = 148;
-        if (int rc = fused_blocks_per_sm(p->n1, p->n2, &bps)) return bail(rc);
+        if (int rc = fused_blocks_per_sm(p->n1, p->n2, &bps, p->fused_tma)) return bail(rc);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         if (const char *e = getenv("HPXFFT_B200_FUSED_BPS")) { int v = atoi(e); if (v >= 1 && v < bps) bps = v; }
         p->fused_grid = (unsigned) (bps * sms);
@@ -788,6 +814,13 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         CUB(cudaMalloc(&p->tw_col, t.size() * sizeof(double2)));
         CUB(cudaMemcpyAsync(p->tw_col, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
         CUB(cudaStreamSynchronize(p->stream));
+        if (p->two_level) {
+            std::vector<double2> w2;
+            make_interlevel(w2, t, p->n1, p->n2);
+            CUB(cudaMalloc(&p->tw_il, w2.size() * sizeof(double2)));
+            CUB(cudaMemcpyAsync(p->tw_il, w2.data(), w2.size() * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
+            CUB(cudaStreamSynchronize(p->stream));
+        }
     }
 
     if (nranks > 1) {
@@ -820,6 +853,7 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     if (p->two_level)
         snprintf(buf, sizeof(buf), "c2c columns: n=%zu four-step %u x %u on %d-column tiles (level A strided + twiddle, level B contiguous)%s",
                  p->nx, p->n1, p->n2, CW, p->fused ? ", fused persistent launch with L2-resident scratch ring" : "");
+    if (p->fused_tma) p->col_desc_extra = " [producer warp: cp.async.bulk + mbarrier]";
     else
         snprintf(buf, sizeof(buf), "c2c columns: n=%zu single Stockham tile FFT on %d-column tiles", p->nx, CW);
     p->col_desc = buf;
@@ -963,7 +997,7 @@ int hpxfft_b200_write_plans(const hpxfft_b200_plan *p, const char *file_path)
     if (!f) return fail(HPXFFT_B200_EINVAL, "Failed to open file: %s", file_path);
     // same two-section structure as core/src/shared/loop.cpp:203-209
     fprintf(f, "FFTW r2c 1D plan:\n(hpxfft_b200 sm_100a %s)\n", p->row_desc.c_str());
-    fprintf(f, "FFTW c2c 1D plan:\n(hpxfft_b200 sm_100a %s)\n\n", p->col_desc.c_str());
+    fprintf(f, "FFTW c2c 1D plan:\n(hpxfft_b200 sm_100a %s%s)\n\n", p->col_desc.c_str(), p->col_desc_extra.c_str());
     fclose(f);
     return 0;
 }
@@ -1092,8 +1126,9 @@ int hpxfft_b200_c2c_cols(double *host_data, size_t n, size_t width, int device)
         cudaFree(p->bufB);
         cudaFree(p->S);
         cudaFree(p->tw_col);
+        cudaFree(p->tw_il);
         if (p->stream) cudaStreamDestroy(p->stream);
-        p->bufB = nullptr; p->S = nullptr; p->tw_col = nullptr; p->stream = nullptr;
+        p->bufB = nullptr; p->S = nullptr; p->tw_col = nullptr; p->tw_il = nullptr; p->stream = nullptr;
     };
 #define CUC(call)                                                                                        \
     do {                                                                                                 \
@@ -1110,6 +1145,12 @@ int hpxfft_b200_c2c_cols(double *host_data, size_t n, size_t width, int device)
     if (p->two_level) CUC(cudaMalloc(&p->S, tbytes));
     CUC(cudaMalloc(&p->tw_col, t.size() * sizeof(double2)));
     CUC(cudaMemcpyAsync(p->tw_col, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
+    std::vector<double2> w2;
+    if (p->two_level) {
+        make_interlevel(w2, t, p->n1, p->n2);
+        CUC(cudaMalloc(&p->tw_il, w2.size() * sizeof(double2)));
+        CUC(cudaMemcpyAsync(p->tw_il, w2.data(), w2.size() * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
+    }
     CUC(cudaMemcpyAsync(A, host_data, bytes, cudaMemcpyHostToDevice, p->stream));
     tile_kernel<<<148 * 4, 256, 0, p->stream>>>(A, p->bufB, (unsigned) n, (unsigned) width);
     CUC(cudaGetLastError());

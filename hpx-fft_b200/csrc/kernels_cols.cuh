@@ -5,13 +5,17 @@
 // instead of transposing so that x becomes contiguous, a CTA owns a tile of CW = 16 adjacent ky
 // columns and runs the FFT down the rows.  All global accesses are 256-byte segments, the shared
 // memory tile is [point][column] with the column index fastest across threads, which makes every
-// shared-memory access conflict-free without padding.
+// shared-memory access conflict-free without padding.  Twiddles never come from global memory inside
+// the butterfly loops: the per-pass factors live in a small shared-memory table built once per CTA and
+// the inter-level factors w_nx^(k1*x2) are one contiguous row of a precomputed [x2][k1] table.
 //
 // nx <= 256        : one Stockham FFT per tile (cols_single_kernel).
-// nx = n1*n2 > 256 : four-step.  Level A (cols_levelA_kernel): for every x2, FFT over x1 (stride n2
-//                    rows), multiply by w_nx^(k1*x2), write scratch S[ct][k1][x2][c].  Level B
-//                    (cols_levelB_kernel): for every k1, FFT over x2 (contiguous in S), result row is
-//                    kx = k1 + n1*k2, written straight to its final position (ColDst).
+// nx = n1*n2 > 256 : four-step.  Level A: for every x2, FFT over x1 (stride n2 rows), multiply by
+//                    w_nx^(k1*x2), write scratch S[strip][k1][x2][c].  Level B: for every k1, FFT over x2
+//                    (contiguous in S), result row kx = k1 + n1*k2 goes straight to its final position.
+//                    Run as two launches (cols_levelA/B_kernel, S = full array in HBM) or fused in one
+//                    persistent launch whose scratch ring stays in L2 (cols_fused_kernel and the
+//                    warp-specialised TMA-bulk/mbarrier variant cols_fused_tma_kernel).
 #pragma once
 #include "layout.cuh"
 
@@ -29,11 +33,52 @@ __host__ __device__ constexpr int col_radix(int N, int p)
 }
 __host__ __device__ constexpr int col_pt(int N) { return N < 16 ? N : 16; }       // points per thread
 __host__ __device__ constexpr int col_threads(int N) { return (N / col_pt(N)) * CW; }
-__host__ __device__ constexpr size_t col_smem_bytes(int N) { return N <= 16 ? 0 : (size_t) N * CW * sizeof(cd); }
+// shared-memory twiddle table: pass p >= 1 holds w_{NS*R}^(r*k) at [k*R + r], k < NS (= product of earlier radices)
+__host__ __device__ constexpr int col_tw_entries(int N)
+{
+    return col_npass(N) == 1 ? 0 : (col_npass(N) == 2 ? N : col_radix(N, 0) * col_radix(N, 1) + N);
+}
+__host__ __device__ constexpr size_t col_tile_bytes(int N) { return N <= 16 ? 0 : (size_t) N * CW * sizeof(cd); }
+__host__ __device__ constexpr size_t col_tw_bytes(int N) { return (size_t) col_tw_entries(N) * sizeof(cd); }
 
-template <int N, int PT, int R, int NS, bool FIRST, bool LAST, class LD, class ST>
-__device__ __forceinline__ void col_pass(cd (&v)[PT], cd *smem, const cd *__restrict__ tw, unsigned tws, LD &ld, ST &st,
-                                         int u, int c, bool active)
+// CTA-wide barrier (BAR_THREADS == 0) or named barrier 1 over the first BAR_THREADS threads (warp-
+// specialised kernels whose producer warp must not take part)
+template <int BAR_THREADS> __device__ __forceinline__ void tile_barrier()
+{
+    if constexpr (BAR_THREADS == 0)
+        __syncthreads();
+    else
+        asm volatile("bar.sync 1, %0;" ::"n"(BAR_THREADS) : "memory");
+}
+
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// Fills the per-pass twiddle table of a length-N tile FFT from the global table w_L^i (L = N * tws).
+// Call with all `nthreads` participating threads, then barrier before the first tile_fft.
+template <int N> __device__ __forceinline__ void fill_pass_twiddles(cd *ptw, const cd *__restrict__ tw, unsigned tws, int tid, int nthreads)
+{
+    constexpr int NP = col_npass(N);
+    if constexpr (NP >= 2) {
+        constexpr int R0 = col_radix(N, 0), R1 = col_radix(N, 1);
+        for (int i = tid; i < R0 * R1; i += nthreads) {
+            const int k = i / R1, r = i - k * R1;
+            ptw[i] = ldtw(tw, (unsigned) (r * k * (N / (R0 * R1))) * tws);
+        }
+        if constexpr (NP == 3) {
+            constexpr int R2 = col_radix(N, 2);
+            for (int i = tid; i < N; i += nthreads) {
+                const int k = i / R2, r = i - k * R2;
+                ptw[R0 * R1 + i] = ldtw(tw, (unsigned) (r * k) * tws); // NS*R == N: stride 1 in the length-N table
+            }
+        }
+    }
+}
+
+template <int N, int PT, int R, int NS, bool FIRST, bool LAST, int BAR_THREADS, class LD, class ST, class HOOK>
+__device__ __forceinline__ void col_pass(cd (&v)[PT], cd *smem, const cd *ptw, LD &ld, ST &st, int u, int c, bool active,
+                                         HOOK &after_load)
 {
     constexpr int NB = PT / R, T = N / R, U = N / PT;
     constexpr int LGR = ilog2(R);
@@ -50,38 +95,40 @@ __device__ __forceinline__ void col_pass(cd (&v)[PT], cd *smem, const cd *__rest
             }
         }
     }
-    if (!FIRST && !LAST) __syncthreads(); // every thread has read its inputs before the in-place overwrite
+    if (FIRST) after_load();                          // inputs are in registers: the source buffer may be refilled
+    if (!FIRST && !LAST) tile_barrier<BAR_THREADS>(); // every thread has read its inputs before the in-place overwrite
     if (active) {
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        const int j = u + b * U;
-        const int k = j & (NS - 1);
-        cd w[R];
+        for (int b = 0; b < NB; ++b) {
+            const int j = u + b * U;
+            const int k = j & (NS - 1);
+            cd w[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) w[r] = v[b * R + r];
-        if (NS > 1) {
+            for (int r = 0; r < R; ++r) w[r] = v[b * R + r];
+            if (NS > 1) {
 #pragma unroll
-            for (int r = 1; r < R; ++r) w[r] = cmul(w[r], ldtw(tw, (unsigned) (r * k * (N / (NS * R))) * tws));
-        }
-        fft_dif<R>(w);
-        const int j0 = ((j - k) << LGR) + k; // (j / NS) * NS * R + k
+                for (int r = 1; r < R; ++r) w[r] = cmul(w[r], ptw[k * R + r]);
+            }
+            fft_dif<R>(w);
+            const int j0 = ((j - k) << LGR) + k; // (j / NS) * NS * R + k
 #pragma unroll
-        for (int s = 0; s < R; ++s) {
-            const int o = j0 + s * NS;
-            if (LAST)
-                st(o, c, w[bitrev(s, LGR)]);
-            else
-                smem[o * CW + c] = w[bitrev(s, LGR)];
+            for (int s = 0; s < R; ++s) {
+                const int o = j0 + s * NS;
+                if (LAST)
+                    st(o, c, w[bitrev(s, LGR)]);
+                else
+                    smem[o * CW + c] = w[bitrev(s, LGR)];
+            }
         }
     }
-    }
-    if (!LAST) __syncthreads();
+    if (!LAST) tile_barrier<BAR_THREADS>();
 }
 
-// One length-N forward FFT down each of the CW columns of a tile.  blockDim.x >= col_threads(N);
-// threads beyond col_threads(N) only take part in the barriers.
-template <int N, class LD, class ST>
-__device__ __forceinline__ void tile_fft(cd *smem, const cd *__restrict__ tw, unsigned tws, LD &ld, ST &st)
+// One length-N forward FFT down each of the CW columns of a tile.  Needs >= col_threads(N) threads in
+// the barrier group; threads beyond col_threads(N) only take part in the barriers.
+// smem: tile buffer (col_tile_bytes(N)); ptw: table filled by fill_pass_twiddles<N>.
+template <int N, int BAR_THREADS = 0, class LD, class ST, class HOOK = NoHook>
+__device__ __forceinline__ void tile_fft(cd *smem, const cd *ptw, LD &ld, ST &st, HOOK after_load = HOOK())
 {
     constexpr int PT = col_pt(N);
     constexpr int NP = col_npass(N);
@@ -90,49 +137,59 @@ __device__ __forceinline__ void tile_fft(cd *smem, const cd *__restrict__ tw, un
     const bool active = threadIdx.x < col_threads(N);
     cd v[PT];
     if constexpr (NP == 1) {
-        col_pass<N, PT, R0, 1, true, true>(v, smem, tw, tws, ld, st, u, c, active);
+        col_pass<N, PT, R0, 1, true, true, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load);
     } else if constexpr (NP == 2) {
         constexpr int R1 = col_radix(N, 1);
-        col_pass<N, PT, R0, 1, true, false>(v, smem, tw, tws, ld, st, u, c, active);
-        col_pass<N, PT, R1, R0, false, true>(v, smem, tw, tws, ld, st, u, c, active);
+        col_pass<N, PT, R0, 1, true, false, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load);
+        col_pass<N, PT, R1, R0, false, true, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load);
     } else {
         constexpr int R1 = col_radix(N, 1), R2 = col_radix(N, 2);
-        col_pass<N, PT, R0, 1, true, false>(v, smem, tw, tws, ld, st, u, c, active);
-        col_pass<N, PT, R1, R0, false, false>(v, smem, tw, tws, ld, st, u, c, active);
-        col_pass<N, PT, R2, R0 * R1, false, true>(v, smem, tw, tws, ld, st, u, c, active);
+        col_pass<N, PT, R0, 1, true, false, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load);
+        col_pass<N, PT, R1, R0, false, false, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load);
+        col_pass<N, PT, R2, R0 * R1, false, true, BAR_THREADS>(v, smem, ptw + R0 * R1, ld, st, u, c, active, after_load);
     }
 }
 
 // ---- nx <= 256: whole column in one tile -------------------------------------------------------
+template <int N> __host__ __device__ constexpr size_t single_smem_bytes() { return col_tile_bytes(N) + col_tw_bytes(N); }
+
 template <int N>
 __global__ void __launch_bounds__(col_threads(N)) cols_single_kernel(InterView in, ColDst out, const cd *__restrict__ tw)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd *smem = reinterpret_cast<cd *>(smem_raw);
+    cd *ptw = reinterpret_cast<cd *>(smem_raw + col_tile_bytes(N));
+    fill_pass_twiddles<N>(ptw, tw, 1u, (int) threadIdx.x, col_threads(N));
+    if (col_npass(N) > 1) __syncthreads();
     const unsigned ct = blockIdx.x;
     auto ld = [&](int i, int c) -> cd { return ld_stream(inter_ptr(in, (unsigned) i, ct, (unsigned) c)); };
     auto st = [&](int k, int c, cd val) {
         const unsigned kl = ct * CW + c;
         if (kl < out.w) st_stream(coldst_ptr(out, (unsigned) k, kl), val);
     };
-    tile_fft<N>(smem, tw, 1u, ld, st);
+    tile_fft<N>(smem, ptw, ld, st);
 }
 
 // ---- four-step level A: FFT over x1 for fixed x2, then inter-level twiddle ----------------------
+// W2[x2][k1] = w_nx^(k1*x2)
+template <int N1> __host__ __device__ constexpr size_t levelA_smem_bytes() { return col_tile_bytes(N1) + col_tw_bytes(N1) + N1 * sizeof(cd); }
+
 template <int N1>
 __global__ void __launch_bounds__(col_threads(N1))
-    cols_levelA_kernel(InterView in, cd *__restrict__ S, unsigned n2, const cd *__restrict__ tw)
+    cols_levelA_kernel(InterView in, cd *__restrict__ S, unsigned n2, const cd *__restrict__ tw, const cd *__restrict__ W2)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd *smem = reinterpret_cast<cd *>(smem_raw);
+    cd *ptw = reinterpret_cast<cd *>(smem_raw + col_tile_bytes(N1));
+    cd *wil = ptw + col_tw_entries(N1);
     const unsigned x2 = blockIdx.x, ct = blockIdx.y;
+    fill_pass_twiddles<N1>(ptw, tw, n2, (int) threadIdx.x, col_threads(N1));
+    for (int i = threadIdx.x; i < N1; i += col_threads(N1)) wil[i] = ldtw(W2, x2 * (unsigned) N1 + (unsigned) i);
+    __syncthreads();
     cd *Sct = S + (unsigned long long) ct * N1 * n2 * CW;
     auto ld = [&](int i, int c) -> cd { return ld_stream(inter_ptr(in, (unsigned) i * n2 + x2, ct, (unsigned) c)); };
-    auto st = [&](int k1, int c, cd val) {
-        const cd w = ldtw(tw, (unsigned) k1 * x2); // w_nx^(k1*x2)
-        Sct[((unsigned long long) k1 * n2 + x2) * CW + c] = cmul(val, w);
-    };
-    tile_fft<N1>(smem, tw, n2, ld, st);
+    auto st = [&](int k1, int c, cd val) { Sct[((unsigned long long) k1 * n2 + x2) * CW + c] = cmul(val, wil[k1]); };
+    tile_fft<N1>(smem, ptw, ld, st);
 }
 
 // ---- four-step level B: FFT over x2 for fixed k1, output row kx = k1 + n1*k2 ---------------------
@@ -142,6 +199,9 @@ __global__ void __launch_bounds__(col_threads(N2))
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd *smem = reinterpret_cast<cd *>(smem_raw);
+    cd *ptw = reinterpret_cast<cd *>(smem_raw + col_tile_bytes(N2));
+    fill_pass_twiddles<N2>(ptw, tw, n1, (int) threadIdx.x, col_threads(N2));
+    if (col_npass(N2) > 1) __syncthreads();
     const unsigned k1 = blockIdx.x, ct = blockIdx.y;
     const cd *Sk = S + ((unsigned long long) ct * n1 + k1) * N2 * CW;
     auto ld = [&](int i, int c) -> cd { return Sk[(unsigned) i * CW + c]; };
@@ -149,7 +209,7 @@ __global__ void __launch_bounds__(col_threads(N2))
         const unsigned kl = ct * CW + c;
         if (kl < out.w) st_stream(coldst_ptr(out, k1 + n1 * (unsigned) k2, kl), val);
     };
-    tile_fft<N2>(smem, tw, n1, ld, st);
+    tile_fft<N2>(smem, ptw, ld, st);
 }
 
 // ---- fused four-step: level A and level B in ONE persistent launch, intermediate kept in L2 -------
@@ -175,16 +235,15 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void cta_wait_count(const unsigned *p, unsigned target)
+__device__ __forceinline__ unsigned claim_tile(unsigned *counter)
 {
-    if (threadIdx.x == 0) {
-        while (ld_acquire_u32(p) < target) __nanosleep(64);
-    }
-    __syncthreads();
+    unsigned t;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(counter) : "memory");
+    return t;
 }
-__device__ __forceinline__ void cta_signal(unsigned *p)
+template <int BAR_THREADS> __device__ __forceinline__ void cta_signal(unsigned *p)
 {
-    __syncthreads(); // all of this CTA's stores are issued (and its smem tile is free again)
+    tile_barrier<BAR_THREADS>(); // all of this CTA's stores are issued (and its smem tile is free again)
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(p, 1u);
@@ -195,34 +254,39 @@ template <int N1, int N2> __host__ __device__ constexpr int fused_threads()
 {
     return col_threads(N1) > col_threads(N2) ? col_threads(N1) : col_threads(N2);
 }
+template <int N1, int N2> __host__ __device__ constexpr size_t fused_tile_bytes()
+{
+    return col_tile_bytes(N1) > col_tile_bytes(N2) ? col_tile_bytes(N1) : col_tile_bytes(N2);
+}
+// tile | pass twiddles N1 | pass twiddles N2 | inter-level row
 template <int N1, int N2> __host__ __device__ constexpr size_t fused_smem_bytes()
 {
-    return col_smem_bytes(N1) > col_smem_bytes(N2) ? col_smem_bytes(N1) : col_smem_bytes(N2);
+    return fused_tile_bytes<N1, N2>() + col_tw_bytes(N1) + col_tw_bytes(N2) + N1 * sizeof(cd);
 }
-
 // resident CTAs per SM the register allocator is asked to make room for
 template <int N1, int N2> __host__ __device__ constexpr int fused_min_blocks()
 {
     return fused_threads<N1, N2>() <= 128 ? 5 : (fused_threads<N1, N2>() <= 256 ? 2 : 1);
 }
 
-__device__ __forceinline__ unsigned claim_tile(unsigned *counter)
-{
-    unsigned t;
-    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(counter) : "memory");
-    return t;
-}
-
 template <int N1, int N2>
 __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, N2>())
-    cols_fused_kernel(InterView in, cd *__restrict__ S, ColDst out, const cd *__restrict__ tw, unsigned ntiles, FusedCtl ctl)
+    cols_fused_kernel(InterView in, cd *__restrict__ S, ColDst out, const cd *__restrict__ tw, const cd *__restrict__ W2, unsigned ntiles,
+                      FusedCtl ctl)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NT = fused_threads<N1, N2>();
     cd *smem = reinterpret_cast<cd *>(smem_raw);
+    cd *ptw1 = reinterpret_cast<cd *>(smem_raw + fused_tile_bytes<N1, N2>());
+    cd *ptw2 = ptw1 + col_tw_entries(N1);
+    cd *wil = ptw2 + col_tw_entries(N2);
     __shared__ unsigned s_tile;
     constexpr unsigned PER_GROUP = N1 + N2;
     const unsigned total = (ntiles + ctl.lag) * PER_GROUP;
     const unsigned long long slot_elems = (unsigned long long) N1 * N2 * CW;
+
+    fill_pass_twiddles<N1>(ptw1, tw, (unsigned) N2, (int) threadIdx.x, NT);
+    fill_pass_twiddles<N2>(ptw2, tw, (unsigned) N1, (int) threadIdx.x, NT);
 
     // dependency of tile t: (counter address, target) -- nullptr when there is none
     auto dep_of = [&](unsigned t, unsigned &target) -> const unsigned * {
@@ -271,14 +335,12 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
             // level A: tile x2 = r of strip g
             if (g < ntiles) {
                 const unsigned x2 = r, ct = g;
+                for (int i = threadIdx.x; i < N1; i += NT) wil[i] = ldtw(W2, x2 * (unsigned) N1 + (unsigned) i);
                 cd *Sct = S + (unsigned long long) (g % ctl.nslot) * slot_elems;
                 auto ld = [&](int i, int c) -> cd { return ld_stream(inter_ptr(in, (unsigned) i * N2 + x2, ct, (unsigned) c)); };
-                auto st = [&](int k1, int c, cd val) {
-                    const cd w = ldtw(tw, (unsigned) k1 * x2);
-                    st_cg(Sct + ((unsigned long long) k1 * N2 + x2) * CW + c, cmul(val, w));
-                };
-                tile_fft<N1>(smem, tw, (unsigned) N2, ld, st);
-                cta_signal(ctl.doneA + g);
+                auto st = [&](int k1, int c, cd val) { st_cg(Sct + ((unsigned long long) k1 * N2 + x2) * CW + c, cmul(val, wil[k1])); };
+                tile_fft<N1>(smem, ptw1, ld, st);
+                cta_signal<0>(ctl.doneA + g);
                 did = true;
             }
         } else if (g >= ctl.lag) {
@@ -290,8 +352,8 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
                 const unsigned kl = ct * CW + c;
                 if (kl < out.w) st_stream(coldst_ptr(out, k1 + (unsigned) N1 * (unsigned) k2, kl), val);
             };
-            tile_fft<N2>(smem, tw, (unsigned) N1, ld, st);
-            cta_signal(ctl.doneB + ct);
+            tile_fft<N2>(smem, ptw2, ld, st);
+            cta_signal<0>(ctl.doneB + ct);
             did = true;
         }
         if (!did) __syncthreads(); // keep s_tile stable until every thread has read it
@@ -301,6 +363,179 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
             dep_ptr = next_ptr;
             dep_seen = next_seen;
             dep_target = next_target;
+        }
+    }
+}
+
+// ---- warp-specialised fused four-step: TMA bulk copies + mbarriers -------------------------------
+//
+// Same tile order, dependency counters and L2-resident scratch ring as cols_fused_kernel, but the tile
+// that a CTA will work on next is already being copied into a shared-memory staging buffer by a
+// dedicated producer warp (cp.async.bulk, completion on an mbarrier) while the consumer warps are
+// still computing the current tile.  The producer also owns the tile claim and the dependency wait,
+// so none of those latencies is seen by the math warps.  Level-B tiles are one contiguous 16*N2*CW-byte
+// bulk copy out of the scratch ring; level-A tiles are N1 copies of one CW*16-byte row segment each,
+// plus the N1*16-byte row of inter-level twiddles.
+namespace ptx {
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE_%=;\n"
+        "bra MBAR_WAIT_%=;\n"
+        "MBAR_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+}  // namespace ptx
+
+template <int N1, int N2> __host__ __device__ constexpr int tma_consumer_threads() { return fused_threads<N1, N2>(); }
+template <int N1, int N2> __host__ __device__ constexpr int tma_threads() { return fused_threads<N1, N2>() + 32; }
+// stage | tile | pass twiddles N1 | pass twiddles N2 | inter-level rows (double-buffered)
+template <int N1, int N2> __host__ __device__ constexpr size_t tma_smem_bytes()
+{
+    return 2 * fused_tile_bytes<N1, N2>() + col_tw_bytes(N1) + col_tw_bytes(N2) + 2 * N1 * sizeof(cd);
+}
+template <int N1, int N2> __host__ __device__ constexpr int tma_min_blocks()
+{
+    return tma_smem_bytes<N1, N2>() <= 74 * 1024 ? 3 : (tma_smem_bytes<N1, N2>() <= 112 * 1024 ? 2 : 1);
+}
+
+template <int N1, int N2>
+__global__ void __launch_bounds__(tma_threads<N1, N2>(), tma_min_blocks<N1, N2>())
+    cols_fused_tma_kernel(InterView in, cd *__restrict__ S, ColDst out, const cd *__restrict__ tw, const cd *__restrict__ W2, unsigned ntiles,
+                          FusedCtl ctl)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NCT = tma_consumer_threads<N1, N2>();
+    constexpr unsigned PER_GROUP = N1 + N2;
+    constexpr unsigned END = 0xffffffffu;
+    cd *stage = reinterpret_cast<cd *>(smem_raw);
+    cd *tile = reinterpret_cast<cd *>(smem_raw + fused_tile_bytes<N1, N2>());
+    cd *ptw1 = reinterpret_cast<cd *>(smem_raw + 2 * fused_tile_bytes<N1, N2>());
+    cd *ptw2 = ptw1 + col_tw_entries(N1);
+    cd *wil = ptw2 + col_tw_entries(N2); // [2][N1]
+    __shared__ __align__(8) unsigned long long full_bar, empty_bar;
+    __shared__ unsigned s_info;
+    const unsigned total = (ntiles + ctl.lag) * PER_GROUP;
+    const unsigned long long slot_elems = (unsigned long long) N1 * N2 * CW;
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(&full_bar, 1);
+        ptx::mbar_init(&empty_bar, NCT);
+        ptx::fence_mbar_init();
+    }
+    if (threadIdx.x < NCT) {
+        fill_pass_twiddles<N1>(ptw1, tw, (unsigned) N2, (int) threadIdx.x, NCT);
+        fill_pass_twiddles<N2>(ptw2, tw, (unsigned) N1, (int) threadIdx.x, NCT);
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= NCT) {
+        // ================= producer warp =================
+        const unsigned lane = threadIdx.x - NCT;
+        unsigned parity_e = 1; // the staging buffer starts out free
+        unsigned wsel = 0;     // inter-level twiddle buffer the next level-A tile will use
+        for (;;) {
+            // claim the next non-empty tile
+            unsigned t = 0, g = 0, r = 0;
+            bool isA = false;
+            for (;;) {
+                if (lane == 0) t = claim_tile(ctl.counter);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (t >= total) break;
+                g = t / PER_GROUP;
+                r = t - g * PER_GROUP;
+                isA = r < (unsigned) N2;
+                if (isA ? (g < ntiles) : (g >= ctl.lag)) break;
+            }
+            if (t >= total) {
+                if (lane == 0) {
+                    ptx::mbar_wait(&empty_bar, parity_e);
+                    s_info = END;
+                    ptx::mbar_arrive(&full_bar);
+                }
+                break;
+            }
+            // dependency: level B needs its strip's level-A tiles; level A needs its scratch slot drained
+            if (lane == 0) {
+                if (isA) {
+                    if (g >= ctl.nslot)
+                        while (ld_acquire_u32(ctl.doneB + (g - ctl.nslot)) < (unsigned) N1) __nanosleep(64);
+                } else {
+                    while (ld_acquire_u32(ctl.doneA + (g - ctl.lag)) < (unsigned) N2) __nanosleep(64);
+                }
+                ptx::mbar_wait(&empty_bar, parity_e);
+                s_info = t;
+                ptx::mbar_arrive_expect_tx(&full_bar, (unsigned) (isA ? (N1 * CW + N1) * sizeof(cd) : N2 * CW * sizeof(cd)));
+            }
+            parity_e ^= 1u;
+            __syncwarp();
+            if (isA) {
+                const unsigned x2 = r, ct = g;
+                for (unsigned i = lane; i < (unsigned) N1; i += 32)
+                    ptx::bulk_g2s(stage + i * CW, inter_ptr(in, i * N2 + x2, ct, 0u), CW * sizeof(cd), &full_bar);
+                if (lane == 0) ptx::bulk_g2s(wil + wsel * N1, W2 + (unsigned long long) x2 * N1, N1 * sizeof(cd), &full_bar);
+                wsel ^= 1u;
+            } else if (lane == 0) {
+                const unsigned k1 = r - N2, ct = g - ctl.lag;
+                const cd *Sk = S + (unsigned long long) (ct % ctl.nslot) * slot_elems + (unsigned long long) k1 * N2 * CW;
+                ptx::bulk_g2s(stage, Sk, (unsigned) (N2 * CW * sizeof(cd)), &full_bar);
+            }
+        }
+    } else {
+        // ================= consumer warps =================
+        unsigned parity_f = 0, wsel = 0;
+        auto release_stage = [&]() { ptx::mbar_arrive(&empty_bar); };
+        for (;;) {
+            ptx::mbar_wait(&full_bar, parity_f);
+            parity_f ^= 1u;
+            const unsigned t = s_info;
+            if (t == END) break;
+            const unsigned g = t / PER_GROUP, r = t - g * PER_GROUP;
+            auto ld = [&](int i, int c) -> cd { return stage[i * CW + c]; };
+            if (r < (unsigned) N2) {
+                const unsigned x2 = r;
+                const cd *w = wil + wsel * N1;
+                wsel ^= 1u;
+                cd *Sct = S + (unsigned long long) (g % ctl.nslot) * slot_elems;
+                auto st = [&](int k1, int c, cd val) { st_cg(Sct + ((unsigned long long) k1 * N2 + x2) * CW + c, cmul(val, w[k1])); };
+                tile_fft<N1, NCT>(tile, ptw1, ld, st, release_stage);
+                cta_signal<NCT>(ctl.doneA + g);
+            } else {
+                const unsigned k1 = r - N2, ct = g - ctl.lag;
+                auto st = [&](int k2, int c, cd val) {
+                    const unsigned kl = ct * CW + c;
+                    if (kl < out.w) st_stream(coldst_ptr(out, k1 + (unsigned) N1 * (unsigned) k2, kl), val);
+                };
+                tile_fft<N2, NCT>(tile, ptw2, ld, st, release_stage);
+                cta_signal<NCT>(ctl.doneB + ct);
+            }
         }
     }
 }
