@@ -183,21 +183,22 @@ template <class K> int set_smem(K kernel, size_t bytes)
     return 0;
 }
 
-template <int M, int C = 1> int launch_rows_big(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+template <int M, int C, bool FAST> int launch_rows_big_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
 {
-    constexpr size_t smem = row_smem_bytes<M>();
+    constexpr size_t smem = row_smem_total<M>();
     static int configured = -1;
     if (configured != p->device) {
-        if (int rc = set_smem(rows_r2c_kernel<M, C>, smem)) return rc;
+        if (int rc = set_smem(rows_r2c_kernel<M, C, FAST>, smem)) return rc;
         configured = p->device;
     }
     const unsigned ngroups = (nrows + row_group<M>() - 1) / row_group<M>();
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
-    const unsigned cap = (unsigned) (4 * sms) / C > 0 ? (unsigned) (4 * sms) / C : 1u;
+    // one resident CTA per SM (shared memory bound): persistent CTAs amortise the twiddle-table build
+    const unsigned cap = (unsigned) sms / C > 0 ? (unsigned) sms / C : 1u;
     const unsigned grid = ngroups < cap ? ngroups : cap;
     if (C > 2 && !p->zraw) return fail(HPXFFT_B200_ESTATE, "long-row scratch missing");
-    rows_r2c_kernel<M, C><<<dim3(grid, C), ROW_THREADS, smem, p->stream>>>(V, pitch, nrows, dst, p->tw_row, p->zraw);
+    rows_r2c_kernel<M, C, FAST><<<dim3(grid, C), ROW_THREADS, smem, p->stream>>>(V, pitch, nrows, dst, p->tw_row, p->zraw);
     CU(cudaGetLastError());
     if (C > 2) {
         const unsigned m = (unsigned) M * C;
@@ -205,6 +206,15 @@ template <int M, int C = 1> int launch_rows_big(const hpxfft_b200_plan *p, const
         CU(cudaGetLastError());
     }
     return 0;
+}
+
+template <int M, int C = 1> int launch_rows_big(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+{
+    // fast output addressing: one destination rank and tile-aligned per-s stride (the 1-GPU hot configs)
+    if constexpr (M == 8192 && C <= 2) {
+        if (dst.P == 1) return launch_rows_big_t<M, C, true>(p, dst, nrows, V, pitch);
+    }
+    return launch_rows_big_t<M, C, false>(p, dst, nrows, V, pitch);
 }
 
 template <int M> int launch_rows_tiny(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
@@ -346,6 +356,14 @@ int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const Co
     ctl.doneB = p->ctl + 1 + ntiles;
     ctl.lag = p->lag;
     ctl.nslot = p->nslot;
+    {
+        static int discard = -1;
+        if (discard < 0) {
+            const char *e = getenv("HPXFFT_B200_DISCARD");
+            discard = (e && e[0] == '0') ? 0 : 1;
+        }
+        ctl.discard = (unsigned) discard;
+    }
     if (p->fused_tma)
         cols_fused_tma_kernel<N1, N2><<<p->fused_grid, tma_threads<N1, N2>(), tma_smem_bytes<N1, N2>(), p->stream>>>(in, p->S, out, p->tw_col,
                                                                                                           p->tw_il, ntiles, ctl);

@@ -227,6 +227,7 @@ struct FusedCtl {
     unsigned *doneA;   // [ntiles] finished level-A tiles per strip
     unsigned *doneB;   // [ntiles] finished level-B tiles per strip
     unsigned lag, nslot;
+    unsigned discard; // level-B tiles discard their scratch lines from L2 after reading them
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
@@ -241,6 +242,13 @@ __device__ __forceinline__ unsigned claim_tile(unsigned *counter)
     asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(counter) : "memory");
     return t;
 }
+// Drops a consumed 128-byte scratch line from L2 without writing it back: level-B tiles are the only
+// readers of the level-A output, so once read the line is dead and its write-back would be pure waste.
+__device__ __forceinline__ void l2_discard_line(const void *p)
+{
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
+
 template <int BAR_THREADS> __device__ __forceinline__ void cta_signal(unsigned *p)
 {
     tile_barrier<BAR_THREADS>(); // all of this CTA's stores are issued (and its smem tile is free again)
@@ -353,6 +361,11 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
                 if (kl < out.w) st_stream(coldst_ptr(out, k1 + (unsigned) N1 * (unsigned) k2, kl), val);
             };
             tile_fft<N2>(smem, ptw2, ld, st);
+            if (ctl.discard) {
+                // every thread's loads of this tile have been consumed (two barriers ago): retire the lines
+                for (int ln = threadIdx.x; ln < N2 * CW * (int) sizeof(cd) / 128; ln += NT)
+                    l2_discard_line(reinterpret_cast<const char *>(Sk) + (size_t) ln * 128);
+            }
             cta_signal<0>(ctl.doneB + ct);
             did = true;
         }

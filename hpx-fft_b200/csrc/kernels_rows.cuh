@@ -69,10 +69,21 @@ __device__ __forceinline__ cd load_split(const cd *__restrict__ zrow, int idx, i
     }
 }
 
+// ---- shared-memory twiddle tables of the row kernel (built once per persistent CTA) ---------------
+//   tw1[r*R0 + k]  = w_{R0 R1}^(r k)          second prefix pass (k < R0, r < R1), only when NPRE == 2
+//   tw2[r*JW + j]  = w_M^(r j)                last pass, r < 16, j <= PP/2 (column PP-j uses the conjugate:
+//                                             w_M^(r (PP-j)) = w_16^r conj(w_M^(r j)), and the w_16^r factor
+//                                             only rotates the butterfly's output index by one)
+//   tw3[j]         = w_n^(c + C j)            Hermitian split, j <= PP/2; the s-dependence is w_32^s, a constant
+template <int M> __host__ __device__ constexpr int row_jw() { return M / 32 + 1; }
+template <int M> __host__ __device__ constexpr int row_tw1_entries() { return RowPlan<M>::NPRE == 2 ? RowPlan<M>::R0 * RowPlan<M>::R1 : 0; }
+template <int M> __host__ __device__ constexpr int row_tw_entries() { return row_tw1_entries<M>() + 17 * row_jw<M>(); }
+template <int M> __host__ __device__ constexpr size_t row_smem_total() { return row_smem_bytes<M>() + (size_t) row_tw_entries<M>() * sizeof(cd); }
+
 // one prefix pass: radix R, NS = product of earlier radices
 template <int M, int C, int R, int NS, bool FIRST>
-__device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__restrict__ zrow, const cd *__restrict__ tw, int lt,
-                                         int c)
+__device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__restrict__ zrow, const cd *__restrict__ tw, const cd *tw1,
+                                         int lt, int c)
 {
     constexpr int PS = RowPlan<M>::PS;
     constexpr int NB = ROW_PT / R, T = M / R, TPR = row_tpr<M>();
@@ -98,7 +109,7 @@ __device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__re
         for (int r = 0; r < R; ++r) w[r] = v[b * R + r];
         if (NS > 1) {
 #pragma unroll
-            for (int r = 1; r < R; ++r) w[r] = cmul(w[r], ldtw(tw, (unsigned) (r * k) * (unsigned) (2 * C * M / (NS * R))));
+            for (int r = 1; r < R; ++r) w[r] = cmul(w[r], tw1[r * NS + k]);
         }
         fft_dif<R>(w);
         const int j0 = ((j - k) << LGR) + k;
@@ -108,11 +119,12 @@ __device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__re
     __syncthreads();
 }
 
-// tw: w_n^i, i < n = 2*M*C.  V rows have `pitch` complex (= cy) elements.  grid = (row groups, C).
+// tw: w_n^i, i < n = 2*M*C.  V rows have `pitch` complex (= cy) elements.  grid = (persistent CTAs, C).
 // C <= 2: Hermitian split fused (the partner of Z[c + C k2] lives in the same CTA); output via RowDst.
 // C  > 2: the partner lives in CTA C-c, so the raw Z is written to `zraw` (row-major, pitch m = M*C) and
 //         herm_split_kernel finishes the job.
-template <int M, int C>
+// FASTADDR: single destination rank and 16 | C*PP -- output pointers advance by a constant per s.
+template <int M, int C, bool FASTADDR>
 __global__ void __launch_bounds__(ROW_THREADS, 1)
     rows_r2c_kernel(const cd *__restrict__ V, unsigned pitch, unsigned nxl, RowDst dst, const cd *__restrict__ tw, cd *__restrict__ zraw)
 {
@@ -120,23 +132,40 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
     using P = RowPlan<M>;
     constexpr int PS = P::PS, TPR = row_tpr<M>(), G = row_group<M>(), LP = row_lp<M>();
     constexpr int PP = M / 16; // columns of the last pass
+    constexpr int JW = row_jw<M>();
     constexpr unsigned MM = (unsigned) M * C; // complex length of the whole row
     const int g = threadIdx.x / TPR, lt = threadIdx.x % TPR;
     const int c = C == 1 ? 0 : (int) blockIdx.y;
     cd *sm = reinterpret_cast<cd *>(smem_raw) + g * LP;
+    cd *tw1 = reinterpret_cast<cd *>(smem_raw + row_smem_bytes<M>());
+    cd *tw2 = tw1 + row_tw1_entries<M>();
+    cd *tw3 = tw2 + 16 * JW;
     const unsigned ngroups = (nxl + G - 1) / G;
 
+    // build the twiddle tables (the first row_pass barrier publishes them)
+    if constexpr (P::NPRE == 2) {
+        for (int i = threadIdx.x; i < P::R0 * P::R1; i += ROW_THREADS) {
+            const int r = i / P::R0, k = i - r * P::R0;
+            tw1[i] = ldtw(tw, (unsigned) (r * k) * (unsigned) (2 * C * M / (P::R0 * P::R1)));
+        }
+    }
+    for (int i = threadIdx.x; i < 16 * JW; i += ROW_THREADS) {
+        const int r = i / JW, j = i - r * JW;
+        tw2[i] = ldtw(tw, (unsigned) (2 * C) * (unsigned) (r * j));
+    }
+    for (int i = threadIdx.x; i < JW; i += ROW_THREADS) tw3[i] = ldtw(tw, (unsigned) c + (unsigned) C * (unsigned) i);
+
+    const bool odd = (C == 2 && c == 1);
     for (unsigned grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const unsigned row = grp * G + g;
         const bool valid = row < nxl;
         const cd *zrow = V + (unsigned long long) (valid ? row : nxl - 1) * pitch;
         cd v[ROW_PT];
-        row_pass<M, C, P::R0, 1, true>(v, sm, zrow, tw, lt, c);
-        if constexpr (P::NPRE == 2) row_pass<M, C, P::R1, P::R0, false>(v, sm, zrow, tw, lt, c);
+        row_pass<M, C, P::R0, 1, true>(v, sm, zrow, tw, tw1, lt, c);
+        if constexpr (P::NPRE == 2) row_pass<M, C, P::R1, P::R0, false>(v, sm, zrow, tw, tw1, lt, c);
 
         // ---- last pass: two radix-16 butterflies (columns jA, jB) ----
         // partner of k2 is M - k2 (c == 0) or M - 1 - k2 (C == 2, c == 1)
-        const bool odd = (C == 2 && c == 1);
         const int jA = lt, jB = odd ? PP - 1 - lt : (lt ? PP - lt : PP / 2);
         cd A[16], B[16];
 #pragma unroll
@@ -144,35 +173,70 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
             A[r] = sm[rpad<PS>(jA + r * PP)];
             B[r] = sm[rpad<PS>(jB + r * PP)];
         }
+        // rotated == column jB got conj twiddles, its natural output s sits at butterfly output (s+1)&15
+        const bool rotated = odd || lt != 0;
+        if (odd) {
 #pragma unroll
-        for (int r = 1; r < 16; ++r) {
-            A[r] = cmul(A[r], ldtw(tw, (unsigned) (2 * C) * (unsigned) (r * jA)));
-            B[r] = cmul(B[r], ldtw(tw, (unsigned) (2 * C) * (unsigned) (r * jB)));
+            for (int r = 1; r < 16; ++r) {
+                A[r] = cmul(A[r], tw2[r * JW + jA]);
+                B[r] = cmulc(B[r], tw2[r * JW + jA + 1]); // jB = PP - (jA + 1)
+            }
+        } else if (lt != 0) {
+#pragma unroll
+            for (int r = 1; r < 16; ++r) {
+                const cd t = tw2[r * JW + jA];
+                A[r] = cmul(A[r], t);
+                B[r] = cmulc(B[r], t);
+            }
+        } else {
+#pragma unroll
+            for (int r = 1; r < 16; ++r) B[r] = mulw32(B[r], r); // jA = 0, jB = PP/2: w_M^(r PP/2) = w_32^r
         }
         fft_dif<16>(A);
         fft_dif<16>(B);
-        // natural order: Z[c + C*(j + s*PP)] = X_[bitrev(s)]
+        // natural order: Z[c + C*(jA + s*PP)] = A[bitrev(s)],  Z[c + C*(jB + s*PP)] = B[bitrev(rotated ? s+1 : s)]
         if constexpr (C > 2) {
             if (valid) {
                 cd *zr = zraw + (unsigned long long) row * MM;
 #pragma unroll
-                for (int s = 0; s < 16; ++s) {
-                    st_stream(zr + (unsigned) c + (unsigned) C * (unsigned) (jA + s * PP), A[bitrev(s, 4)]);
-                    st_stream(zr + (unsigned) c + (unsigned) C * (unsigned) (jB + s * PP), B[bitrev(s, 4)]);
+                for (int s = 0; s < 16; ++s) st_stream(zr + (unsigned) c + (unsigned) C * (unsigned) (jA + s * PP), A[bitrev(s, 4)]);
+                if (rotated) {
+#pragma unroll
+                    for (int s = 0; s < 16; ++s)
+                        st_stream(zr + (unsigned) c + (unsigned) C * (unsigned) (jB + s * PP), B[bitrev((s + 1) & 15, 4)]);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 16; ++s) st_stream(zr + (unsigned) c + (unsigned) C * (unsigned) (jB + s * PP), B[bitrev(s, 4)]);
                 }
             }
-        } else if (odd || lt != 0) {
+        } else if (rotated) {
+            const cd wb = tw3[jA]; // w_n^(c + C jA)
+            cd *pk = nullptr, *pm = nullptr;
+            long long step = 0;
+            if constexpr (FASTADDR) {
+                const unsigned k0 = (unsigned) c + (unsigned) C * (unsigned) jA, m0 = MM - k0;
+                pk = dst.base[0] + (unsigned long long) (k0 >> 4) * dst.tile_stride + (unsigned long long) row * CW + (k0 & 15u);
+                pm = dst.base[0] + (unsigned long long) (m0 >> 4) * dst.tile_stride + (unsigned long long) row * CW + (m0 & 15u);
+                step = (long long) ((C * PP) >> 4) * (long long) dst.tile_stride;
+            }
 #pragma unroll
             for (int s = 0; s < 16; ++s) {
-                const unsigned kA = (unsigned) c + (unsigned) C * (unsigned) (jA + s * PP);
                 cd xk, xmk;
-                herm_pair(A[bitrev(s, 4)], B[bitrev(15 - s, 4)], ldtw(tw, kA), xk, xmk);
+                // pair Z[kA] with Z[MM - kA] = natural output 15-s of column jB = butterfly output (16-s)&15
+                herm_pair(A[bitrev(s, 4)], B[bitrev((16 - s) & 15, 4)], mulw32(wb, s), xk, xmk);
                 if (valid) {
-                    st_stream(rowdst_ptr(dst, row, kA), xk);
-                    st_stream(rowdst_ptr(dst, row, MM - kA), xmk);
+                    if constexpr (FASTADDR) {
+                        st_stream(pk + s * step, xk);
+                        st_stream(pm - s * step, xmk);
+                    } else {
+                        const unsigned kA = (unsigned) c + (unsigned) C * (unsigned) (jA + s * PP);
+                        st_stream(rowdst_ptr(dst, row, kA), xk);
+                        st_stream(rowdst_ptr(dst, row, MM - kA), xmk);
+                    }
                 }
             }
         } else {
+            // lt == 0, c == 0: columns 0 and PP/2 are their own partners
             const cd z0 = A[0];
             if (valid) {
                 st_stream(rowdst_ptr(dst, row, 0u), make_double2(z0.x + z0.y, 0.0));
@@ -182,18 +246,19 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
             for (int s = 1; s < 8; ++s) {
                 const unsigned k = (unsigned) C * (unsigned) (s * PP);
                 cd xk, xmk;
-                herm_pair(A[bitrev(s, 4)], A[bitrev(16 - s, 4)], ldtw(tw, k), xk, xmk);
+                herm_pair(A[bitrev(s, 4)], A[bitrev(16 - s, 4)], mulw32(make_double2(1.0, 0.0), s), xk, xmk);
                 if (valid) {
                     st_stream(rowdst_ptr(dst, row, k), xk);
                     st_stream(rowdst_ptr(dst, row, MM - k), xmk);
                 }
             }
             if (valid) st_stream(rowdst_ptr(dst, row, (unsigned) C * (unsigned) (8 * PP)), cconj(A[bitrev(8, 4)]));
+            const cd wh = tw3[PP / 2]; // w_n^(C PP/2)
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
                 const unsigned k = (unsigned) C * (unsigned) (PP / 2 + s * PP);
                 cd xk, xmk;
-                herm_pair(B[bitrev(s, 4)], B[bitrev(15 - s, 4)], ldtw(tw, k), xk, xmk);
+                herm_pair(B[bitrev(s, 4)], B[bitrev(15 - s, 4)], mulw32(wh, s), xk, xmk);
                 if (valid) {
                     st_stream(rowdst_ptr(dst, row, k), xk);
                     st_stream(rowdst_ptr(dst, row, MM - k), xmk);
