@@ -58,6 +58,7 @@ struct NcclApi {
     void *handle = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *) = nullptr; // optional
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -87,6 +88,7 @@ int nccl_load()
     NSYM(Recv, "ncclRecv")
     NSYM(AllReduce, "ncclAllReduce")
 #undef NSYM
+    *(void **) (&g_nccl.CommInitRankConfig) = dlsym(h, "ncclCommInitRankConfig");
     g_nccl.handle = h;
     return 0;
 }
@@ -157,6 +159,12 @@ struct hpxfft_b200_plan {
     // p2p
     std::vector<void *> peerI, peerV;
     bool ipc_imported = false;
+    // pipelined exchange (NCCL modes): sub-slab chunks of rows / strips, communication on its own stream
+    int chunks_r = 1, chunks_c = 1;
+    cd *bufC = nullptr;             // receive buffer of exchange #2 when it overlaps the column pass
+    cudaStream_t cstream = nullptr; // high-priority communication stream
+    std::vector<cudaEvent_t> ev_chunk; // [chunks_r + chunks_c + 2]
+    int sm_reserve = 0;             // SMs left free for NCCL's kernels while the row kernel runs
     // execution
     cudaStream_t stream = nullptr;
     // One event set per execute since the last reset (ring of EV_SETS): lets a benchmark launch K
@@ -195,6 +203,7 @@ template <int M, int C, bool FAST> int launch_rows_big_t(const hpxfft_b200_plan 
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
     // one resident CTA per SM (shared memory bound): persistent CTAs amortise the twiddle-table build
+    sms -= p->sm_reserve;
     const unsigned cap = (unsigned) sms / C > 0 ? (unsigned) sms / C : 1u;
     const unsigned grid = ngroups < cap ? ngroups : cap;
     if (C > 2 && !p->zraw) return fail(HPXFFT_B200_ESTATE, "long-row scratch missing");
@@ -340,7 +349,7 @@ template <int N1, int N2> int fused_occupancy(int *blocks_per_sm, bool tma)
 }
 
 template <int N1, int N2>
-int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles)
+int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ct0, unsigned ntiles)
 {
     constexpr size_t smem = fused_smem_bytes<N1, N2>();
     static int configured = -1;
@@ -356,6 +365,8 @@ int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const Co
     ctl.doneB = p->ctl + 1 + ntiles;
     ctl.lag = p->lag;
     ctl.nslot = p->nslot;
+    ctl.ct0 = ct0;
+    if (ctl.nslot > ntiles) ctl.nslot = ntiles; // a short chunk needs (and may use) no more slots than strips
     {
         static int discard = -1;
         if (discard < 0) {
@@ -375,9 +386,10 @@ int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const Co
 
 #define FUSED_PAIRS(X) X(32, 16) X(32, 32) X(64, 32) X(64, 64) X(128, 64) X(128, 128) X(256, 128) X(256, 256) X(512, 256) X(512, 512)
 
-int launch_cols_fused(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles)
+int launch_cols_fused(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ct0, unsigned ntiles)
 {
-#define X(A, B) if (p->n1 == A && p->n2 == B) return launch_cols_fused_t<A, B>(p, in, out, ntiles);
+    if (ntiles == 0) return 0;
+#define X(A, B) if (p->n1 == A && p->n2 == B) return launch_cols_fused_t<A, B>(p, in, out, ct0, ntiles);
     FUSED_PAIRS(X)
 #undef X
     return fail(HPXFFT_B200_EINVAL, "no fused column kernel for %u x %u", p->n1, p->n2);
@@ -451,11 +463,11 @@ void fill_coldst(const hpxfft_b200_plan *p, ColDst &d)
         if (r == p->rank) {
             d.base[r] = (cd *) p->V;
             d.pitch[r] = (unsigned) p->cy;
-            d.col0[r] = p->c0;
+            d.col0[r] = (int) p->c0;
         } else if (p->mode == MODE_P2P) {
             d.base[r] = (cd *) p->peerV[r];
             d.pitch[r] = (unsigned) p->cy;
-            d.col0[r] = p->c0;
+            d.col0[r] = (int) p->c0;
         } else {
             d.base[r] = p->bufA + (unsigned long long) r * p->nxl * p->w;
             d.pitch[r] = p->w;
@@ -485,9 +497,10 @@ int exchange1(hpxfft_b200_plan *p)
             NC(g_nccl.Recv(p->bufB + (unsigned long long) from * rblk, rblk * 2, ncclDouble, from, p->comm, p->stream));
         }
         NC(g_nccl.GroupEnd());
-    } else { // scatter: one rooted scatter per locality (core/src/distributed/loop.cpp:158-167)
+    } else { // scatter: one rooted scatter per locality, all in flight together like the reference's
+             // asynchronous scatter_to / scatter_from futures (core/src/distributed/loop.cpp:158-167)
+        NC(g_nccl.GroupStart());
         for (int root = 0; root < P; ++root) {
-            NC(g_nccl.GroupStart());
             if (root == me) {
                 for (int to = 0; to < P; ++to)
                     if (to != me)
@@ -495,8 +508,8 @@ int exchange1(hpxfft_b200_plan *p)
             } else {
                 NC(g_nccl.Recv(p->bufB + (unsigned long long) root * rblk, rblk * 2, ncclDouble, root, p->comm, p->stream));
             }
-            NC(g_nccl.GroupEnd());
         }
+        NC(g_nccl.GroupEnd());
     }
     return 0;
 }
@@ -516,8 +529,8 @@ int exchange2(hpxfft_b200_plan *p)
         }
         NC(g_nccl.GroupEnd());
     } else {
+        NC(g_nccl.GroupStart());
         for (int root = 0; root < P; ++root) {
-            NC(g_nccl.GroupStart());
             if (root == me) {
                 for (int to = 0; to < P; ++to)
                     if (to != me)
@@ -526,9 +539,169 @@ int exchange2(hpxfft_b200_plan *p)
                 NC(g_nccl.Recv(p->bufB + (unsigned long long) p->nxl * p->c0_of[root],
                             (unsigned long long) p->nxl * p->w_of[root] * 2, ncclDouble, root, p->comm, p->stream));
             }
-            NC(g_nccl.GroupEnd());
+        }
+        NC(g_nccl.GroupEnd());
+    }
+    return 0;
+}
+
+// strip range [t0, t1) and column range of chunk t when `ntiles` strips / `w` columns are cut into `nch` chunks
+void chunk_bounds(unsigned ntiles, unsigned w, int nch, int t, unsigned &t0, unsigned &t1, unsigned &col0, unsigned &wc)
+{
+    const unsigned per = (ntiles + nch - 1) / nch;
+    t0 = (unsigned) t * per < ntiles ? (unsigned) t * per : ntiles;
+    t1 = (unsigned) (t + 1) * per < ntiles ? (unsigned) (t + 1) * per : ntiles;
+    col0 = t0 * CW;
+    const unsigned cend = t1 * CW < w ? t1 * CW : w;
+    wc = cend > col0 ? cend - col0 : 0;
+}
+
+// group of sends/recvs of one exchange chunk; `order` = rotation (all_to_all) or root-major (scatter)
+template <class SendFn, class RecvFn> int exchange_group(hpxfft_b200_plan *p, SendFn send, RecvFn recv)
+{
+    const int P = p->P, me = p->rank;
+    NC(g_nccl.GroupStart());
+    if (p->mode == MODE_ALL_TO_ALL) {
+        for (int s = 1; s < P; ++s) {
+            if (int rc = send((me + s) % P)) return rc;
+            if (int rc = recv((me - s + P) % P)) return rc;
+        }
+    } else {
+        for (int root = 0; root < P; ++root) {
+            if (root == me) {
+                for (int to = 0; to < P; ++to)
+                    if (to != me)
+                        if (int rc = send(to)) return rc;
+            } else if (int rc = recv(root))
+                return rc;
         }
     }
+    NC(g_nccl.GroupEnd());
+    return 0;
+}
+
+// NCCL modes with sub-slab pipelining: the exchange of row chunk s overlaps the row FFTs of chunk s+1,
+// the exchange (+ unpack) of strip chunk t overlaps the column FFTs of chunk t+1.
+int enqueue_transform_pipelined(hpxfft_b200_plan *p)
+{
+    const int P = p->P, me = p->rank, Sr = p->chunks_r, Sc = p->chunks_c;
+    int launches = 0;
+    const size_t nxs = p->nxl / Sr;
+    cudaEvent_t *ev = p->evs.data() + (size_t) (p->nrec % hpxfft_b200_plan::EV_SETS) * hpxfft_b200_plan::EV_PER_SET;
+    p->nrec += 1;
+    cudaEvent_t *evr = p->ev_chunk.data(), *evc = p->ev_chunk.data() + Sr;
+    cudaEvent_t ev_x1 = p->ev_chunk[Sr + Sc], ev_x2 = p->ev_chunk[Sr + Sc + 1];
+
+    std::vector<unsigned long long> soff(P + 1, 0);
+    for (int q = 0; q < P; ++q) soff[q + 1] = soff[q] + (unsigned long long) p->ntiles_of[q] * p->nxl * CW;
+    const unsigned long long rblk = (unsigned long long) p->ntiles * p->nxl * CW;
+
+    CU(cudaEventRecord(ev[0], p->stream));
+    // the communication stream must not start before everything previously enqueued on the main stream
+    CU(cudaStreamWaitEvent(p->cstream, ev[0], 0));
+    // ---- dimension 1: row chunks, each followed by its exchange on the communication stream
+    for (int s = 0; s < Sr; ++s) {
+        RowDst rd;
+        rd.tile_stride = (unsigned long long) nxs * CW;
+        rd.cy = (unsigned) p->cy;
+        rd.wq0 = p->wq0;
+        rd.P = (unsigned) P;
+        for (int q = 0; q < P; ++q) {
+            const unsigned long long cs = (unsigned long long) p->ntiles_of[q] * nxs * CW; // chunk stride inside q's block
+            rd.base[q] = (q == me ? p->bufB + (unsigned long long) me * rblk : p->bufA + soff[q]) + (unsigned long long) s * cs;
+        }
+        if (int rc = launch_rows(p, rd, (unsigned) nxs, (const cd *) p->V + (size_t) s * nxs * p->cy, (unsigned) p->cy, p->m)) return rc;
+        launches += 1 + (p->m > 16384 ? 1 : 0);
+        CU(cudaEventRecord(evr[s], p->stream));
+        CU(cudaStreamWaitEvent(p->cstream, evr[s], 0));
+        auto send = [&](int to) -> int {
+            const unsigned long long cs = (unsigned long long) p->ntiles_of[to] * nxs * CW;
+            NC(g_nccl.Send(p->bufA + soff[to] + (unsigned long long) s * cs, cs * 2, ncclDouble, to, p->comm, p->cstream));
+            return 0;
+        };
+        auto recv = [&](int from) -> int {
+            const unsigned long long cs = (unsigned long long) p->ntiles * nxs * CW;
+            NC(g_nccl.Recv(p->bufB + (unsigned long long) from * rblk + (unsigned long long) s * cs, cs * 2, ncclDouble, from, p->comm,
+                           p->cstream));
+            return 0;
+        };
+        if (int rc = exchange_group(p, send, recv)) return rc;
+    }
+    CU(cudaEventRecord(ev[1], p->stream));
+    CU(cudaEventRecord(ev_x1, p->cstream));
+    CU(cudaStreamWaitEvent(p->stream, ev_x1, 0));
+    CU(cudaEventRecord(ev[2], p->stream));
+    CU(cudaEventRecord(ev[6], p->stream));
+
+    // ---- dimension 2: strip chunks
+    InterView iv;
+    iv.base = p->bufB;
+    iv.nxl = (unsigned) nxs; // I is chunk-major: [r][s][ct][js][c] == [x / nxs][ct][x % nxs][c]
+    iv.tile_stride = (unsigned long long) nxs * CW;
+    iv.rank_stride = (unsigned long long) p->ntiles * nxs * CW;
+    for (int t = 0; t < Sc; ++t) {
+        unsigned t0, t1, col0, wc;
+        chunk_bounds(p->ntiles, p->w, Sc, t, t0, t1, col0, wc);
+        if (t1 > t0) {
+            ColDst cdst;
+            cdst.nxl = (unsigned) p->nxl;
+            cdst.w = p->w;
+            const unsigned long long boff = (unsigned long long) P * p->nxl * col0;
+            for (int r = 0; r < P; ++r) {
+                if (r == me) {
+                    cdst.base[r] = (cd *) p->V;
+                    cdst.pitch[r] = (unsigned) p->cy;
+                    cdst.col0[r] = (int) p->c0;
+                } else {
+                    cdst.base[r] = p->bufA + boff + (unsigned long long) r * p->nxl * wc;
+                    cdst.pitch[r] = wc;
+                    cdst.col0[r] = -(int) col0;
+                }
+            }
+            if (Sc == 1 && !p->fused) {
+                if (int rc = launch_cols(p, iv, cdst, p->ntiles, p->S, (unsigned) p->nx, p->n1, p->n2, p->two_level, &launches, nullptr)) return rc;
+            } else {
+                if (int rc = launch_cols_fused(p, iv, cdst, t0, t1 - t0)) return rc;
+                launches += 1;
+            }
+        }
+        CU(cudaEventRecord(evc[t], p->stream));
+        CU(cudaStreamWaitEvent(p->cstream, evc[t], 0));
+        UnpackChunk u;
+        bool any = false;
+        for (int q = 0; q < P; ++q) {
+            unsigned q0, q1, qcol0, qwc;
+            chunk_bounds(p->ntiles_of[q], p->w_of[q], Sc, t, q0, q1, qcol0, qwc);
+            u.src_off[q] = (unsigned long long) p->nxl * (p->c0_of[q] + qcol0);
+            u.dst_col[q] = p->c0_of[q] + qcol0;
+            u.wc[q] = q == me ? 0 : qwc;
+            any = any || u.wc[q] > 0;
+        }
+        auto send = [&](int to) -> int {
+            if (wc == 0) return 0;
+            const unsigned long long boff = (unsigned long long) P * p->nxl * col0;
+            NC(g_nccl.Send(p->bufA + boff + (unsigned long long) to * p->nxl * wc, (unsigned long long) p->nxl * wc * 2, ncclDouble, to,
+                           p->comm, p->cstream));
+            return 0;
+        };
+        auto recv = [&](int from) -> int {
+            if (u.wc[from] == 0) return 0;
+            NC(g_nccl.Recv(p->bufC + u.src_off[from], (unsigned long long) p->nxl * u.wc[from] * 2, ncclDouble, from, p->comm, p->cstream));
+            return 0;
+        };
+        if (int rc = exchange_group(p, send, recv)) return rc;
+        if (any) {
+            unpack_chunk_kernel<<<dim3((unsigned) p->nxl, (unsigned) P), 256, 0, p->cstream>>>(p->bufC, (cd *) p->V, (unsigned) p->cy, u);
+            CU(cudaGetLastError());
+            launches += 1;
+        }
+    }
+    CU(cudaEventRecord(ev[3], p->stream));
+    CU(cudaEventRecord(ev_x2, p->cstream));
+    CU(cudaStreamWaitEvent(p->stream, ev_x2, 0));
+    CU(cudaEventRecord(ev[4], p->stream));
+    CU(cudaEventRecord(ev[5], p->stream));
+    p->launches = launches;
     return 0;
 }
 
@@ -536,6 +709,7 @@ int enqueue_transform(hpxfft_b200_plan *p)
 {
     if (p->mode == MODE_P2P && p->P > 1 && !p->ipc_imported)
         return fail(HPXFFT_B200_ESTATE, "p2p plan: hpxfft_b200_ipc_import has not been called");
+    if (p->P > 1 && p->mode != MODE_P2P && (p->chunks_r > 1 || p->chunks_c > 1)) return enqueue_transform_pipelined(p);
     int launches = 0;
     RowDst rd;
     fill_rowdst(p, rd);
@@ -565,7 +739,7 @@ int enqueue_transform(hpxfft_b200_plan *p)
     // phase 3: c2c columns (+ fused split / transpose)        -> second_fftw
     if (p->fused) {
         CU(cudaEventRecord(ev[6], p->stream));
-        if (int rc = launch_cols_fused(p, iv, cdst, p->ntiles)) return rc;
+        if (int rc = launch_cols_fused(p, iv, cdst, 0u, p->ntiles)) return rc;
         launches += 1;
     } else if (int rc = launch_cols(p, iv, cdst, p->ntiles, p->S, (unsigned) p->nx, p->n1, p->n2, p->two_level, &launches, ev[6]))
         return rc;
@@ -684,6 +858,13 @@ void hpxfft_b200_destroy(hpxfft_b200_plan *p)
         }
     }
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
+    for (auto &e : p->ev_chunk)
+        if (e) cudaEventDestroy(e);
+    if (p->cstream) {
+        cudaStreamSynchronize(p->cstream);
+        cudaStreamDestroy(p->cstream);
+    }
+    cudaFree(p->bufC);
     cudaFree(p->V);
     cudaFree(p->bufA);
     cudaFree(p->bufB);
@@ -785,12 +966,23 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         // N = 512 tiles need 2 x 128 KB with a staging buffer: fall back to the plain fused kernel
         if (p->n1 > 256 || p->n2 > 256) p->fused_tma = false;
     }
+    if (nranks > 1 && mode != MODE_P2P) {
+        // Sub-slab pipelining of the NCCL exchanges is implemented and parity-tested but OFF by default:
+        // NCCL's copy kernels need >= 32 CTAs for full NVLink rate, which the persistent FFT kernels
+        // cannot spare without losing more than the overlap wins.
+        int want = 1;
+        if (const char *e = getenv("HPXFFT_B200_CHUNKS")) want = atoi(e) > 0 ? atoi(e) : 1;
+        if (want > 1) {
+            p->sm_reserve = 16;
+            if (const char *e = getenv("HPXFFT_B200_SM_RESERVE")) { int v = atoi(e); if (v >= 0 && v <= 64) p->sm_reserve = v; }
+        }
+    }
     if (p->fused) {
         int bps = 1, sms = 148;
         if (int rc = fused_blocks_per_sm(p->n1, p->n2, &bps, p->fused_tma)) return bail(rc);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         if (const char *e = getenv("HPXFFT_B200_FUSED_BPS")) { int v = atoi(e); if (v >= 1 && v < bps) bps = v; }
-        p->fused_grid = (unsigned) (bps * sms);
+        p->fused_grid = (unsigned) (bps * (sms - p->sm_reserve));
         const unsigned per_group = p->n1 + p->n2;
         p->lag = (unsigned) ((3 * (size_t) p->fused_grid / 2 + per_group - 1) / per_group) + 1;
         if (const char *e = getenv("HPXFFT_B200_LAG")) { int v = atoi(e); if (v >= 1) p->lag = (unsigned) v; }
@@ -841,11 +1033,37 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         }
     }
 
+    if (nranks > 1 && mode != MODE_P2P) {
+        int want = 1;
+        if (const char *e = getenv("HPXFFT_B200_CHUNKS")) want = atoi(e) > 0 ? atoi(e) : 1;
+        int sr = want, sc = want;
+        while (sr > 1 && (p->nxl % sr != 0 || p->nxl / sr < 8)) sr /= 2;
+        if (!p->fused) sc = 1;
+        while (sc > 1 && p->ntiles / sc < 2 * (p->lag + 1)) sc /= 2;
+        p->chunks_r = sr < 1 ? 1 : sr;
+        p->chunks_c = sc < 1 ? 1 : sc;
+        if (p->chunks_r > 1 || p->chunks_c > 1) {
+            CUB(cudaMalloc(&p->bufC, p->nxl * p->cy * sizeof(cd)));
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            CUB(cudaStreamCreateWithPriority(&p->cstream, cudaStreamNonBlocking, hi));
+            p->ev_chunk.assign((size_t) p->chunks_r + p->chunks_c + 2, nullptr);
+            for (auto &e : p->ev_chunk) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+    }
     if (nranks > 1) {
         if (int rc = nccl_load()) return bail(rc);
         ncclUniqueId id;
         memcpy(&id, unique_id, sizeof(id));
-        ncclResult_t r = g_nccl.CommInitRank(&p->comm, nranks, id, rank);
+        ncclResult_t r;
+        if (p->sm_reserve > 0 && g_nccl.CommInitRankConfig) {
+            // keep NCCL's kernels inside the SMs the FFT kernels leave free, so that the overlapped
+            // exchange never evicts a persistent FFT CTA
+            ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+            cfg.maxCTAs = p->sm_reserve;
+            r = g_nccl.CommInitRankConfig(&p->comm, nranks, id, rank, &cfg);
+        } else
+            r = g_nccl.CommInitRank(&p->comm, nranks, id, rank);
         if (r != ncclSuccess) return bail(fail(HPXFFT_B200_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)));
         CUB(cudaMalloc(&p->d_barrier, sizeof(int)));
         CUB(cudaMemsetAsync(p->d_barrier, 0, sizeof(int), p->stream));
@@ -1025,6 +1243,7 @@ void *hpxfft_b200_stream(hpxfft_b200_plan *p) { return p ? (void *) p->stream : 
 int hpxfft_b200_launches_per_execute(const hpxfft_b200_plan *p)
 {
     if (!p) return 0;
+    if (p->launches > 0) return p->launches; // counted by the last execute
     int n = 1 + ((p->two_level && !p->fused) ? 2 : 1) + (p->m > 16384 ? 1 : 0);
     if (p->P > 1 && p->mode != MODE_P2P) n += 1;
     return n;

@@ -228,6 +228,7 @@ struct FusedCtl {
     unsigned *doneB;   // [ntiles] finished level-B tiles per strip
     unsigned lag, nslot;
     unsigned discard; // level-B tiles discard their scratch lines from L2 after reading them
+    unsigned ct0;     // first strip of this launch (chunked column pass); counters / ring slots are launch-local
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
         if (r < (unsigned) N2) {
             // level A: tile x2 = r of strip g
             if (g < ntiles) {
-                const unsigned x2 = r, ct = g;
+                const unsigned x2 = r, ct = ctl.ct0 + g;
                 for (int i = threadIdx.x; i < N1; i += NT) wil[i] = ldtw(W2, x2 * (unsigned) N1 + (unsigned) i);
                 cd *Sct = S + (unsigned long long) (g % ctl.nslot) * slot_elems;
                 auto ld = [&](int i, int c) -> cd { return ld_stream(inter_ptr(in, (unsigned) i * N2 + x2, ct, (unsigned) c)); };
@@ -353,8 +354,8 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
             }
         } else if (g >= ctl.lag) {
             // level B: tile k1 = r - N2 of strip g - lag
-            const unsigned k1 = r - N2, ct = g - ctl.lag;
-            const cd *Sk = S + (unsigned long long) (ct % ctl.nslot) * slot_elems + (unsigned long long) k1 * N2 * CW;
+            const unsigned k1 = r - N2, sl = g - ctl.lag, ct = ctl.ct0 + sl;
+            const cd *Sk = S + (unsigned long long) (sl % ctl.nslot) * slot_elems + (unsigned long long) k1 * N2 * CW;
             auto ld = [&](int i, int c) -> cd { return ld_cg(Sk + (unsigned) i * CW + c); };
             auto st = [&](int k2, int c, cd val) {
                 const unsigned kl = ct * CW + c;
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
                 for (int ln = threadIdx.x; ln < N2 * CW * (int) sizeof(cd) / 128; ln += NT)
                     l2_discard_line(reinterpret_cast<const char *>(Sk) + (size_t) ln * 128);
             }
-            cta_signal<0>(ctl.doneB + ct);
+            cta_signal<0>(ctl.doneB + sl);
             did = true;
         }
         if (!did) __syncthreads(); // keep s_tile stable until every thread has read it
@@ -510,14 +511,14 @@ __global__ void __launch_bounds__(tma_threads<N1, N2>(), tma_min_blocks<N1, N2>(
             parity_e ^= 1u;
             __syncwarp();
             if (isA) {
-                const unsigned x2 = r, ct = g;
+                const unsigned x2 = r, ct = ctl.ct0 + g;
                 for (unsigned i = lane; i < (unsigned) N1; i += 32)
                     ptx::bulk_g2s(stage + i * CW, inter_ptr(in, i * N2 + x2, ct, 0u), CW * sizeof(cd), &full_bar);
                 if (lane == 0) ptx::bulk_g2s(wil + wsel * N1, W2 + (unsigned long long) x2 * N1, N1 * sizeof(cd), &full_bar);
                 wsel ^= 1u;
             } else if (lane == 0) {
-                const unsigned k1 = r - N2, ct = g - ctl.lag;
-                const cd *Sk = S + (unsigned long long) (ct % ctl.nslot) * slot_elems + (unsigned long long) k1 * N2 * CW;
+                const unsigned k1 = r - N2, sl = g - ctl.lag;
+                const cd *Sk = S + (unsigned long long) (sl % ctl.nslot) * slot_elems + (unsigned long long) k1 * N2 * CW;
                 ptx::bulk_g2s(stage, Sk, (unsigned) (N2 * CW * sizeof(cd)), &full_bar);
             }
         }
@@ -541,13 +542,13 @@ __global__ void __launch_bounds__(tma_threads<N1, N2>(), tma_min_blocks<N1, N2>(
                 tile_fft<N1, NCT>(tile, ptw1, ld, st, release_stage);
                 cta_signal<NCT>(ctl.doneA + g);
             } else {
-                const unsigned k1 = r - N2, ct = g - ctl.lag;
+                const unsigned k1 = r - N2, sl = g - ctl.lag, ct = ctl.ct0 + sl;
                 auto st = [&](int k2, int c, cd val) {
                     const unsigned kl = ct * CW + c;
                     if (kl < out.w) st_stream(coldst_ptr(out, k1 + (unsigned) N1 * (unsigned) k2, kl), val);
                 };
                 tile_fft<N2, NCT>(tile, ptw2, ld, st, release_stage);
-                cta_signal<NCT>(ctl.doneB + ct);
+                cta_signal<NCT>(ctl.doneB + sl);
             }
         }
     }

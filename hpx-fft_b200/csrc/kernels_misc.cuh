@@ -58,6 +58,23 @@ __global__ void unpack_kernel(const cd *__restrict__ recv2, cd *__restrict__ V, 
     for (unsigned k = threadIdx.x; k < w; k += blockDim.x) st_stream(dst + k, ld_stream(src + k));
 }
 
+// chunked variant for the pipelined exchange #2: one dense [nxl][wc_q] block per source rank
+struct UnpackChunk {
+    unsigned long long src_off[MAXP]; // element offset of the block inside the receive buffer
+    unsigned dst_col[MAXP];           // first destination column in V
+    unsigned wc[MAXP];                // block width (0 = nothing from this rank)
+};
+// grid = (nxl, P)
+__global__ void unpack_chunk_kernel(const cd *__restrict__ recv, cd *__restrict__ V, unsigned cy, UnpackChunk u)
+{
+    const unsigned j = blockIdx.x, q = blockIdx.y;
+    const unsigned w = u.wc[q];
+    if (w == 0) return;
+    const cd *src = recv + u.src_off[q] + (unsigned long long) j * w;
+    cd *dst = V + (unsigned long long) j * cy + u.dst_col[q];
+    for (unsigned k = threadIdx.x; k < w; k += blockDim.x) st_stream(dst + k, ld_stream(src + k));
+}
+
 // row-major [n][width] complex -> column-tiled I[ct][x][c] (one rank); test / adapter entry points only
 __global__ void tile_kernel(const cd *__restrict__ A, cd *__restrict__ I, unsigned n, unsigned width)
 {

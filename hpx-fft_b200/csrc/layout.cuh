@@ -58,7 +58,7 @@ __device__ __forceinline__ const cd *inter_ptr(const InterView &v, unsigned x, u
 struct ColDst {
     cd *base[MAXP];         // per destination rank r (owner of row kx)
     unsigned pitch[MAXP];   // complex elements per destination row
-    unsigned col0[MAXP];    // first destination column
+    int col0[MAXP];         // destination column of local column 0 (negative inside a chunked send buffer)
     unsigned nxl;           // rows per rank
     unsigned w;             // valid local columns on this rank
 };
@@ -66,7 +66,7 @@ struct ColDst {
 __device__ __forceinline__ cd *coldst_ptr(const ColDst &d, unsigned kx, unsigned kl)
 {
     const unsigned r = kx / d.nxl, j = kx - r * d.nxl;
-    return d.base[r] + (unsigned long long) j * d.pitch[r] + d.col0[r] + kl;
+    return d.base[r] + ((long long) j * (long long) d.pitch[r] + (long long) d.col0[r] + (long long) kl);
 }
 
 }  // namespace hpxfft_b200

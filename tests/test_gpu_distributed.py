@@ -12,6 +12,7 @@ from conftest import gpu_count
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
 CASES = [(64, 64), (16, 256), (256, 512), (1024, 2048), (2048, 64)]
+PIPELINED_CASES = [(1024, 2048), (2048, 512)]   # HPXFFT_B200_CHUNKS=4: sub-slab pipelined exchange
 
 
 def _free_port():
@@ -48,6 +49,21 @@ def _worker(rank, world, port, q):
                 results.append((nx, ny, comm, err * scale, fft.get_measurement("total")))
                 del fft
                 dist.barrier()
+        # opt-in pipelined exchange (row chunks / strip chunks on a second stream)
+        os.environ["HPXFFT_B200_CHUNKS"] = "4"
+        for (nx, ny) in PIPELINED_CASES:
+            nxl = nx // world
+            full = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=12)
+            ref = oracle.fft_2d_r2c_shared(full, workers=2)
+            for comm in ("all_to_all", "scatter"):
+                fft = pkg.distributed.loop(device=rank)
+                fft.initialize(pkg.vector_2d.from_array(full[rank * nxl:(rank + 1) * nxl].copy()), comm, "estimate")
+                out = fft.fft_2d_r2c().data()
+                err = oracle.rel_l2(out, ref[rank * nxl:(rank + 1) * nxl])
+                results.append((nx, ny, comm + "+chunks4", err, fft.get_measurement("total")))
+                del fft
+                dist.barrier()
+        os.environ.pop("HPXFFT_B200_CHUNKS")
         q.put((rank, results))
     except Exception as e:  # pragma: no cover
         import traceback
