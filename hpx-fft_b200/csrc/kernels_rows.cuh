@@ -69,6 +69,22 @@ __device__ __forceinline__ cd load_split(const cd *__restrict__ zrow, int idx, i
     }
 }
 
+// cp.async (LDGSTS) 16-byte global -> shared copy, L2-only caching; used to stage the NEXT row's raw
+// input into the pencil buffer while the current row is still in its register-only tail
+// (last-pass butterflies, Hermitian split, stores)
+__device__ __forceinline__ void cp_async16(cd *dst_smem, const cd *src_gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned) __cvta_generic_to_shared(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int M> __device__ __forceinline__ void stage_row(cd *sm, const cd *__restrict__ zrow, int lt)
+{
+    constexpr int TPR = row_tpr<M>();
+#pragma unroll
+    for (int e = 0; e < ROW_PT; ++e) cp_async16(sm + lt + e * TPR, zrow + lt + e * TPR);
+}
+
 // ---- shared-memory twiddle tables of the row kernel (built once per persistent CTA) ---------------
 //   tw1[r*R0 + k]  = w_{R0 R1}^(r k)          second prefix pass (k < R0, r < R1), only when NPRE == 2
 //   tw2[r*JW + j]  = w_M^(r j)                last pass, r < 16, j <= PP/2 (column PP-j uses the conjugate:
@@ -93,9 +109,12 @@ __device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__re
         const int j = lt + b * TPR;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (FIRST)
-                v[b * R + r] = load_split<M, C>(zrow, j + r * T, c, tw);
-            else
+            if (FIRST) {
+                if constexpr (C == 1)
+                    v[b * R + r] = sm[j + r * T]; // raw row staged by cp.async (identity layout, thread-private)
+                else
+                    v[b * R + r] = load_split<M, C>(zrow, j + r * T, c, tw);
+            } else
                 v[b * R + r] = sm[rpad<PS>(j + r * T)];
         }
     }
@@ -156,11 +175,19 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
     for (int i = threadIdx.x; i < JW; i += ROW_THREADS) tw3[i] = ldtw(tw, (unsigned) c + (unsigned) C * (unsigned) i);
 
     const bool odd = (C == 2 && c == 1);
+    auto row_ptr = [&](unsigned grp) -> const cd * {
+        const unsigned row = grp * G + g;
+        return V + (unsigned long long) (row < nxl ? row : nxl - 1) * pitch;
+    };
+    if constexpr (C == 1) {
+        if (blockIdx.x < ngroups) stage_row<M>(sm, row_ptr(blockIdx.x), lt);
+    }
     for (unsigned grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const unsigned row = grp * G + g;
         const bool valid = row < nxl;
-        const cd *zrow = V + (unsigned long long) (valid ? row : nxl - 1) * pitch;
+        const cd *zrow = row_ptr(grp);
         cd v[ROW_PT];
+        if constexpr (C == 1) cp_async_wait_all(); // own copies landed; each thread only reads what it staged itself
         row_pass<M, C, P::R0, 1, true>(v, sm, zrow, tw, tw1, lt, c);
         if constexpr (P::NPRE == 2) row_pass<M, C, P::R1, P::R0, false>(v, sm, zrow, tw, tw1, lt, c);
 
@@ -172,6 +199,12 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
         for (int r = 0; r < 16; ++r) {
             A[r] = sm[rpad<PS>(jA + r * PP)];
             B[r] = sm[rpad<PS>(jB + r * PP)];
+        }
+        if constexpr (C == 1) {
+            // the pencil buffer is dead until the next row's first pass: refill it with the next row's
+            // raw input while this row finishes in registers
+            __syncthreads();
+            if (grp + gridDim.x < ngroups) stage_row<M>(sm, row_ptr(grp + gridDim.x), lt);
         }
         // rotated == column jB got conj twiddles, its natural output s sits at butterfly output (s+1)&15
         const bool rotated = odd || lt != 0;
