@@ -32,6 +32,7 @@ PROTOTYPES = {
     "hpxfft_b200_synchronize": (C.c_int, [C.c_void_p]),
     "hpxfft_b200_reset_timers": (C.c_int, [C.c_void_p]),
     "hpxfft_b200_transform": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hpxfft_b200_transform_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hpxfft_b200_measurement": (C.c_double, [C.c_void_p, C.c_char_p]),
     "hpxfft_b200_write_plans": (C.c_int, [C.c_void_p, C.c_char_p]),
     "hpxfft_b200_device_ptr": (C.c_void_p, [C.c_void_p]),

@@ -458,6 +458,7 @@ int fill_rowdst(const hpxfft_b200_plan *p, RowDst &d)
 void fill_coldst(const hpxfft_b200_plan *p, ColDst &d)
 {
     d.nxl = (unsigned) p->nxl;
+    d.shift = pow2_shift(d.nxl);
     d.w = p->w;
     for (int r = 0; r < p->P; ++r) {
         if (r == p->rank) {
@@ -637,6 +638,7 @@ int enqueue_transform_pipelined(hpxfft_b200_plan *p)
     InterView iv;
     iv.base = p->bufB;
     iv.nxl = (unsigned) nxs; // I is chunk-major: [r][s][ct][js][c] == [x / nxs][ct][x % nxs][c]
+    iv.shift = pow2_shift(iv.nxl);
     iv.tile_stride = (unsigned long long) nxs * CW;
     iv.rank_stride = (unsigned long long) p->ntiles * nxs * CW;
     for (int t = 0; t < Sc; ++t) {
@@ -645,6 +647,7 @@ int enqueue_transform_pipelined(hpxfft_b200_plan *p)
         if (t1 > t0) {
             ColDst cdst;
             cdst.nxl = (unsigned) p->nxl;
+            cdst.shift = pow2_shift(cdst.nxl);
             cdst.w = p->w;
             const unsigned long long boff = (unsigned long long) P * p->nxl * col0;
             for (int r = 0; r < P; ++r) {
@@ -718,6 +721,7 @@ int enqueue_transform(hpxfft_b200_plan *p)
     InterView iv;
     iv.base = p->bufB;
     iv.nxl = (unsigned) p->nxl;
+    iv.shift = pow2_shift(iv.nxl);
     iv.tile_stride = (unsigned long long) p->nxl * CW;
     iv.rank_stride = (unsigned long long) p->ntiles * p->nxl * CW;
 
@@ -964,7 +968,7 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         p->fused = !(e && e[0] == '0');
         p->fused_tma = p->fused && (e && e[0] == '2'); // HPXFFT_B200_FUSED=2 selects the TMA-bulk/mbarrier variant
         // N = 512 tiles need 2 x 128 KB with a staging buffer: fall back to the plain fused kernel
-        if (p->n1 > 256 || p->n2 > 256) p->fused_tma = false;
+        if (p->n2 < 32) p->fused_tma = false; // single-pass tiles have no shared-memory buffer to refill
     }
     if (nranks > 1 && mode != MODE_P2P) {
         // Sub-slab pipelining of the NCCL exchanges is implemented and parity-tested but OFF by default:
@@ -1219,6 +1223,17 @@ int hpxfft_b200_transform(hpxfft_b200_plan *p, double *host_slab_inout)
     return read_timers(p);
 }
 
+int hpxfft_b200_transform_async(hpxfft_b200_plan *p, double *host_slab_inout)
+{
+    if (!p || !host_slab_inout) return fail(HPXFFT_B200_EINVAL, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    const size_t bytes = p->nxl * p->n_col * sizeof(double);
+    CU(cudaMemcpyAsync(p->V, host_slab_inout, bytes, cudaMemcpyHostToDevice, p->stream));
+    if (int rc = enqueue_transform(p)) return rc;
+    CU(cudaMemcpyAsync(host_slab_inout, p->V, bytes, cudaMemcpyDeviceToHost, p->stream));
+    return 0;
+}
+
 double hpxfft_b200_measurement(const hpxfft_b200_plan *p, const char *key)
 {
     if (!p || !key) return 0.0;
@@ -1394,10 +1409,12 @@ int hpxfft_b200_c2c_cols(double *host_data, size_t n, size_t width, int device)
     InterView iv;
     iv.base = p->bufB;
     iv.nxl = (unsigned) n;
+    iv.shift = pow2_shift(iv.nxl);
     iv.tile_stride = (unsigned long long) n * CW;
     iv.rank_stride = 0;
     ColDst cdst;
     cdst.nxl = (unsigned) n;
+    cdst.shift = pow2_shift(cdst.nxl);
     cdst.w = (unsigned) width;
     cdst.base[0] = A;
     cdst.pitch[0] = (unsigned) width;

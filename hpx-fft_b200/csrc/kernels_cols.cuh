@@ -76,9 +76,9 @@ template <int N> __device__ __forceinline__ void fill_pass_twiddles(cd *ptw, con
     }
 }
 
-template <int N, int PT, int R, int NS, bool FIRST, bool LAST, int BAR_THREADS, class LD, class ST, class HOOK>
+template <int N, int PT, int R, int NS, bool FIRST, bool LAST, int BAR_THREADS, class LD, class ST, class HOOK, class HOOK2>
 __device__ __forceinline__ void col_pass(cd (&v)[PT], cd *smem, const cd *ptw, LD &ld, ST &st, int u, int c, bool active,
-                                         HOOK &after_load)
+                                         HOOK &after_load, HOOK2 &tile_dead)
 {
     constexpr int NB = PT / R, T = N / R, U = N / PT;
     constexpr int LGR = ilog2(R);
@@ -95,7 +95,8 @@ __device__ __forceinline__ void col_pass(cd (&v)[PT], cd *smem, const cd *ptw, L
             }
         }
     }
-    if (FIRST) after_load();                          // inputs are in registers: the source buffer may be refilled
+    if (FIRST) after_load();                          // first-pass inputs are in registers
+    if (LAST) tile_dead();                            // last read of the tile buffer (non-blocking hook)
     if (!FIRST && !LAST) tile_barrier<BAR_THREADS>(); // every thread has read its inputs before the in-place overwrite
     if (active) {
 #pragma unroll
@@ -127,8 +128,8 @@ __device__ __forceinline__ void col_pass(cd (&v)[PT], cd *smem, const cd *ptw, L
 // One length-N forward FFT down each of the CW columns of a tile.  Needs >= col_threads(N) threads in
 // the barrier group; threads beyond col_threads(N) only take part in the barriers.
 // smem: tile buffer (col_tile_bytes(N)); ptw: table filled by fill_pass_twiddles<N>.
-template <int N, int BAR_THREADS = 0, class LD, class ST, class HOOK = NoHook>
-__device__ __forceinline__ void tile_fft(cd *smem, const cd *ptw, LD &ld, ST &st, HOOK after_load = HOOK())
+template <int N, int BAR_THREADS = 0, class LD, class ST, class HOOK = NoHook, class HOOK2 = NoHook>
+__device__ __forceinline__ void tile_fft(cd *smem, const cd *ptw, LD &ld, ST &st, HOOK after_load = HOOK(), HOOK2 tile_dead = HOOK2())
 {
     constexpr int PT = col_pt(N);
     constexpr int NP = col_npass(N);
@@ -137,16 +138,16 @@ __device__ __forceinline__ void tile_fft(cd *smem, const cd *ptw, LD &ld, ST &st
     const bool active = threadIdx.x < col_threads(N);
     cd v[PT];
     if constexpr (NP == 1) {
-        col_pass<N, PT, R0, 1, true, true, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load);
+        col_pass<N, PT, R0, 1, true, true, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load, tile_dead);
     } else if constexpr (NP == 2) {
         constexpr int R1 = col_radix(N, 1);
-        col_pass<N, PT, R0, 1, true, false, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load);
-        col_pass<N, PT, R1, R0, false, true, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load);
+        col_pass<N, PT, R0, 1, true, false, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load, tile_dead);
+        col_pass<N, PT, R1, R0, false, true, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load, tile_dead);
     } else {
         constexpr int R1 = col_radix(N, 1), R2 = col_radix(N, 2);
-        col_pass<N, PT, R0, 1, true, false, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load);
-        col_pass<N, PT, R1, R0, false, false, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load);
-        col_pass<N, PT, R2, R0 * R1, false, true, BAR_THREADS>(v, smem, ptw + R0 * R1, ld, st, u, c, active, after_load);
+        col_pass<N, PT, R0, 1, true, false, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load, tile_dead);
+        col_pass<N, PT, R1, R0, false, false, BAR_THREADS>(v, smem, ptw, ld, st, u, c, active, after_load, tile_dead);
+        col_pass<N, PT, R2, R0 * R1, false, true, BAR_THREADS>(v, smem, ptw + R0 * R1, ld, st, u, c, active, after_load, tile_dead);
     }
 }
 
@@ -387,7 +388,8 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
 // that a CTA will work on next is already being copied into a shared-memory staging buffer by a
 // dedicated producer warp (cp.async.bulk, completion on an mbarrier) while the consumer warps are
 // still computing the current tile.  The producer also owns the tile claim and the dependency wait,
-// so none of those latencies is seen by the math warps.  Level-B tiles are one contiguous 16*N2*CW-byte
+// so none of those latencies is seen by the math warps.  The copies land IN the tile buffer (no staging
+// copy, same shared-memory footprint as the plain kernel).  Level-B tiles are one contiguous 16*N2*CW-byte
 // bulk copy out of the scratch ring; level-A tiles are N1 copies of one CW*16-byte row segment each,
 // plus the N1*16-byte row of inter-level twiddles.
 namespace ptx {
@@ -430,14 +432,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 
 template <int N1, int N2> __host__ __device__ constexpr int tma_consumer_threads() { return fused_threads<N1, N2>(); }
 template <int N1, int N2> __host__ __device__ constexpr int tma_threads() { return fused_threads<N1, N2>() + 32; }
-// stage | tile | pass twiddles N1 | pass twiddles N2 | inter-level rows (double-buffered)
+// tile (refilled in place by the producer) | pass twiddles N1 | pass twiddles N2 | inter-level rows (double-buffered)
 template <int N1, int N2> __host__ __device__ constexpr size_t tma_smem_bytes()
 {
-    return 2 * fused_tile_bytes<N1, N2>() + col_tw_bytes(N1) + col_tw_bytes(N2) + 2 * N1 * sizeof(cd);
+    return fused_tile_bytes<N1, N2>() + col_tw_bytes(N1) + col_tw_bytes(N2) + 2 * N1 * sizeof(cd);
 }
 template <int N1, int N2> __host__ __device__ constexpr int tma_min_blocks()
 {
-    return tma_smem_bytes<N1, N2>() <= 74 * 1024 ? 3 : (tma_smem_bytes<N1, N2>() <= 112 * 1024 ? 2 : 1);
+    return tma_threads<N1, N2>() <= 160 ? 4 : (tma_threads<N1, N2>() <= 288 ? 2 : 1);
 }
 
 template <int N1, int N2>
@@ -449,9 +451,12 @@ __global__ void __launch_bounds__(tma_threads<N1, N2>(), tma_min_blocks<N1, N2>(
     constexpr int NCT = tma_consumer_threads<N1, N2>();
     constexpr unsigned PER_GROUP = N1 + N2;
     constexpr unsigned END = 0xffffffffu;
-    cd *stage = reinterpret_cast<cd *>(smem_raw);
-    cd *tile = reinterpret_cast<cd *>(smem_raw + fused_tile_bytes<N1, N2>());
-    cd *ptw1 = reinterpret_cast<cd *>(smem_raw + 2 * fused_tile_bytes<N1, N2>());
+    // ONE buffer: the producer's bulk copies land where the consumers run the FFT.  The consumers arrive on
+    // empty_bar right after the last pass has read the tile, so the refill for tile i+1 overlaps the
+    // last-pass butterflies, twiddles and stores of tile i without costing any extra shared memory.
+    cd *tile = reinterpret_cast<cd *>(smem_raw);
+    cd *stage = tile;
+    cd *ptw1 = reinterpret_cast<cd *>(smem_raw + fused_tile_bytes<N1, N2>());
     cd *ptw2 = ptw1 + col_tw_entries(N1);
     cd *wil = ptw2 + col_tw_entries(N2); // [2][N1]
     __shared__ __align__(8) unsigned long long full_bar, empty_bar;
@@ -525,7 +530,8 @@ __global__ void __launch_bounds__(tma_threads<N1, N2>(), tma_min_blocks<N1, N2>(
     } else {
         // ================= consumer warps =================
         unsigned parity_f = 0, wsel = 0;
-        auto release_stage = [&]() { ptx::mbar_arrive(&empty_bar); };
+        auto release_stage = [&]() { ptx::mbar_arrive(&empty_bar); };   // tile buffer dead: producer may refill
+        auto inputs_read = [&]() { tile_barrier<NCT>(); };              // in-place first pass: all reads before any write
         for (;;) {
             ptx::mbar_wait(&full_bar, parity_f);
             parity_f ^= 1u;
@@ -539,7 +545,7 @@ __global__ void __launch_bounds__(tma_threads<N1, N2>(), tma_min_blocks<N1, N2>(
                 wsel ^= 1u;
                 cd *Sct = S + (unsigned long long) (g % ctl.nslot) * slot_elems;
                 auto st = [&](int k1, int c, cd val) { st_cg(Sct + ((unsigned long long) k1 * N2 + x2) * CW + c, cmul(val, w[k1])); };
-                tile_fft<N1, NCT>(tile, ptw1, ld, st, release_stage);
+                tile_fft<N1, NCT>(tile, ptw1, ld, st, inputs_read, release_stage);
                 cta_signal<NCT>(ctl.doneA + g);
             } else {
                 const unsigned k1 = r - N2, sl = g - ctl.lag, ct = ctl.ct0 + sl;
@@ -547,7 +553,7 @@ __global__ void __launch_bounds__(tma_threads<N1, N2>(), tma_min_blocks<N1, N2>(
                     const unsigned kl = ct * CW + c;
                     if (kl < out.w) st_stream(coldst_ptr(out, k1 + (unsigned) N1 * (unsigned) k2, kl), val);
                 };
-                tile_fft<N2, NCT>(tile, ptw2, ld, st, release_stage);
+                tile_fft<N2, NCT>(tile, ptw2, ld, st, inputs_read, release_stage);
                 cta_signal<NCT>(ctl.doneB + sl);
             }
         }

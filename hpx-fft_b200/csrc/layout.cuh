@@ -45,11 +45,27 @@ struct InterView {
     unsigned long long rank_stride; // ntiles * nxl * CW
     unsigned long long tile_stride; // nxl * CW
     unsigned nxl;
+    unsigned shift;                 // log2(nxl) when nxl is a power of two, else 0xffffffff
 };
+
+__host__ __device__ inline unsigned pow2_shift(unsigned v)
+{
+    if (v == 0 || (v & (v - 1))) return 0xffffffffu;
+    unsigned s = 0;
+    while ((1u << s) < v) ++s;
+    return s;
+}
 
 __device__ __forceinline__ const cd *inter_ptr(const InterView &v, unsigned x, unsigned ct, unsigned c)
 {
-    const unsigned r = x / v.nxl, j = x - r * v.nxl;
+    unsigned r, j;
+    if (v.shift != 0xffffffffu) {
+        r = x >> v.shift;
+        j = x & (v.nxl - 1);
+    } else {
+        r = x / v.nxl;
+        j = x - r * v.nxl;
+    }
     return v.base + (unsigned long long) r * v.rank_stride + (unsigned long long) ct * v.tile_stride +
            (unsigned long long) j * CW + c;
 }
@@ -61,11 +77,19 @@ struct ColDst {
     int col0[MAXP];         // destination column of local column 0 (negative inside a chunked send buffer)
     unsigned nxl;           // rows per rank
     unsigned w;             // valid local columns on this rank
+    unsigned shift;         // log2(nxl) when nxl is a power of two, else 0xffffffff
 };
 
 __device__ __forceinline__ cd *coldst_ptr(const ColDst &d, unsigned kx, unsigned kl)
 {
-    const unsigned r = kx / d.nxl, j = kx - r * d.nxl;
+    unsigned r, j;
+    if (d.shift != 0xffffffffu) {
+        r = kx >> d.shift;
+        j = kx & (d.nxl - 1);
+    } else {
+        r = kx / d.nxl;
+        j = kx - r * d.nxl;
+    }
     return d.base[r] + ((long long) j * (long long) d.pitch[r] + (long long) d.col0[r] + (long long) kl);
 }
 

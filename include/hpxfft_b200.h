@@ -110,6 +110,10 @@ int hpxfft_b200_synchronize(hpxfft_b200_plan *);
 int hpxfft_b200_reset_timers(hpxfft_b200_plan *);
 /* upload + execute + download in one call: what initialize()+fft_2d_r2c() cost end to end */
 int hpxfft_b200_transform(hpxfft_b200_plan *, double *host_slab_inout);
+/* the same three steps only ENQUEUED on the plan's stream (host_slab_inout must stay valid and should be
+ * page-locked); finish with hpxfft_b200_synchronize.  Two plans driven alternately keep PCIe busy in both
+ * directions: the download of transform i overlaps the upload of transform i+1. */
+int hpxfft_b200_transform_async(hpxfft_b200_plan *, double *host_slab_inout);
 
 /* Replaces loop::get_measurement (core/src/shared/loop.cpp:192, distributed/loop.cpp:350): seconds;
  * keys total, first_fftw, first_trans, second_fftw, second_trans, plan, plan_flops (+ first_split,

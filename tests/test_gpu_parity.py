@@ -147,6 +147,31 @@ def test_transform_end_to_end_and_plan_reuse(pkg, lib, oracle):
     lib.hpxfft_b200_destroy(plan)
 
 
+def test_transform_async_double_buffered(pkg, lib, oracle):
+    """Two plans driven alternately (what bench.py's e2e leg does): every round trip must still be exact."""
+    nx, ny = 256, 1024
+    plans = []
+    for _ in range(2):
+        plan = C.c_void_p()
+        pkg.capi.check(lib.hpxfft_b200_create(C.byref(plan), nx, ny + 2, 0, 1, 0, None, b"estimate", None))
+        plans.append(plan)
+    hosts = [pkg.vector_2d(nx, ny + 2, 0.0, pinned=True) for _ in plans]
+    refs = [None, None]
+    for step in range(6):
+        i = step % 2
+        if step >= 2:
+            pkg.capi.check(lib.hpxfft_b200_synchronize(plans[i]))
+            assert oracle.rel_l2(hosts[i].data(), refs[i]) <= TOL
+        a = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=100 + step)
+        refs[i] = oracle.fft_2d_r2c_shared(a)
+        hosts[i].data()[...] = a
+        pkg.capi.check(lib.hpxfft_b200_transform_async(plans[i], hosts[i].data().ctypes.data))
+    for i in range(2):
+        pkg.capi.check(lib.hpxfft_b200_synchronize(plans[i]))
+        assert oracle.rel_l2(hosts[i].data(), refs[i]) <= TOL
+        lib.hpxfft_b200_destroy(plans[i])
+
+
 def test_write_plans_to_file(pkg, oracle, tmp_path):
     _, fft = shared_fft(pkg, oracle.GOLDEN_4x4_IN)
     path = tmp_path / "plans" / "plan.txt"
