@@ -10,7 +10,7 @@
 
 int main(int argc, char *argv[])
 {
-    cli::options opt(argc, argv, {{"result", "0"}, {"nx", "8"}, {"ny", "16"}, {"plan", "estimate"}, {"run", "scatter"}, {"header", "0"}});
+    cli::options opt(argc, argv, {{"result", "0"}, {"nx", "8"}, {"ny", "14"}, {"plan", "estimate"}, {"run", "scatter"}, {"header", "0"}});
     const std::string run_flag = opt.str("run"), plan_flag = opt.str("plan");
     hpxfft::distributed::loop fft_computer;
     const std::size_t this_locality = fft_computer.this_locality(), num_localities = fft_computer.num_localities();

@@ -143,6 +143,7 @@ struct hpxfft_b200_plan {
     // column FFT decomposition
     unsigned n1 = 1, n2 = 1;
     bool two_level = false;
+    bool rows_generic = false, cols_generic = false; // direct-DFT kernels for lengths that are not powers of two
     // device buffers
     double *V = nullptr;   // slab, nxl x n_col doubles
     cd *bufA = nullptr;    // send buffer of exchange #1 and #2 (nranks > 1, NCCL modes)
@@ -236,6 +237,12 @@ template <int M> int launch_rows_tiny(const hpxfft_b200_plan *p, const RowDst &d
 
 int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m)
 {
+    if (p->rows_generic) {
+        const unsigned ny = (unsigned) (2 * m), cy = ny / 2 + 1;
+        rows_generic_kernel<<<dim3(nrows, (cy + 127) / 128), 128, 0, p->stream>>>((const double *) V, 2 * pitch, nrows, ny, dst, p->tw_row);
+        CU(cudaGetLastError());
+        return 0;
+    }
     switch (m) {
     case 1: return launch_rows_tiny<1>(p, dst, nrows, V, pitch);
     case 2: return launch_rows_tiny<2>(p, dst, nrows, V, pitch);
@@ -315,6 +322,13 @@ template <int N2> int launch_cols_B(const hpxfft_b200_plan *p, const cd *S, cons
 int launch_cols(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles, cd *S, unsigned nx,
                 unsigned n1, unsigned n2, bool two_level, int *launches, cudaEvent_t mid = nullptr)
 {
+    if (p->cols_generic) {
+        if (launches) *launches += 1;
+        if (mid) CU(cudaEventRecord(mid, p->stream));
+        cols_generic_kernel<<<dim3(ntiles * CW, (nx + 127) / 128), 128, 0, p->stream>>>(in, out, nx, p->tw_col);
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (!two_level) {
         if (launches) *launches += 1;
         if (mid) CU(cudaEventRecord(mid, p->stream));
@@ -928,8 +942,16 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         hpxfft_b200_destroy(p);
         return rc;
     };
-    if (!is_pow2(p->m) || p->m > 65536) return bail(fail(HPXFFT_B200_EINVAL, "unsupported ny=%zu: ny/2 must be a power of two <= 65536", p->ny));
-    if (!is_pow2(p->nx) || p->nx > (1u << 18)) return bail(fail(HPXFFT_B200_EINVAL, "unsupported nx=%zu: must be a power of two <= 2^18", p->nx));
+    // powers of two take the Stockham kernels; any other length (FFTW accepts them all, the reference's
+    // default example is 8 x 14) takes the direct-DFT kernels, bounded to sizes where O(n^2) is sane
+    constexpr size_t GENERIC_MAX = 8192;
+    p->rows_generic = !is_pow2(p->m);
+    p->cols_generic = !is_pow2(p->nx);
+    if (p->ny < 2) return bail(fail(HPXFFT_B200_EINVAL, "unsupported ny=%zu", p->ny));
+    if (p->rows_generic ? p->ny > GENERIC_MAX : p->m > 65536)
+        return bail(fail(HPXFFT_B200_EINVAL, "unsupported ny=%zu: ny/2 must be a power of two <= 65536, or ny <= %zu", p->ny, GENERIC_MAX));
+    if (p->cols_generic ? p->nx > GENERIC_MAX : p->nx > (1u << 18))
+        return bail(fail(HPXFFT_B200_EINVAL, "unsupported nx=%zu: must be a power of two <= 2^18, or <= %zu", p->nx, GENERIC_MAX));
     if (p->cy < (size_t) nranks) return bail(fail(HPXFFT_B200_EINVAL, "ny/2+1=%zu columns cannot be split over %d localities", p->cy, nranks));
 
     // column ownership: c_q = q*floor(cy/P), the last rank absorbs cy mod P
@@ -946,6 +968,11 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     p->c0 = p->c0_of[rank];
     p->ntiles = p->ntiles_of[rank];
     choose_col_split(p->nx, p->n1, p->n2, p->two_level);
+    if (p->cols_generic) {
+        p->two_level = false;
+        p->n1 = (unsigned) p->nx;
+        p->n2 = 1;
+    }
 
     cudaEvent_t t0, t1;
     CU(cudaEventCreate(&t0));
@@ -1090,7 +1117,10 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     snprintf(buf, sizeof(buf), "r2c rows: n=%zu via half-length complex Stockham m=%zu (%s), %d points/thread, paired radix-16 last pass + Hermitian split",
              p->ny, p->m, p->m <= 16 ? "register-resident" : "shared-memory pencil", p->m <= 16 ? (int) p->m : ROW_PT);
     p->row_desc = buf;
-    if (p->two_level)
+    if (p->rows_generic) p->row_desc = "r2c rows: direct DFT (length is not a power of two)";
+    if (p->cols_generic)
+        snprintf(buf, sizeof(buf), "c2c columns: n=%zu direct DFT (length is not a power of two)", p->nx);
+    else if (p->two_level)
         snprintf(buf, sizeof(buf), "c2c columns: n=%zu four-step %u x %u on %d-column tiles (level A strided + twiddle, level B contiguous)%s",
                  p->nx, p->n1, p->n2, CW, p->fused ? ", fused persistent launch with L2-resident scratch ring" : "");
     if (p->fused_tma) p->col_desc_extra = " [producer warp: cp.async.bulk + mbarrier]";

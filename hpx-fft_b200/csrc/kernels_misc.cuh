@@ -75,6 +75,48 @@ __global__ void unpack_chunk_kernel(const cd *__restrict__ recv, cd *__restrict_
     for (unsigned k = threadIdx.x; k < w; k += blockDim.x) st_stream(dst + k, ld_stream(src + k));
 }
 
+// ---- generic lengths (any even ny, any nx): direct O(n^2) DFT on the GPU ---------------------------
+// FFTW accepts every length and the reference's default example is 8 x 14 (examples/hpxfft/
+// shared_loop_2d.cpp:142-143).  Sizes that are not powers of two take these kernels -- slow but exact to
+// ~sqrt(n) ulp, and still no CPU fallback.  tw = w_n^i, i < n.
+// grid = (nxl, ceil(cy/128)): one thread per output bin of one row
+__global__ void rows_generic_kernel(const double *__restrict__ V, unsigned n_col, unsigned nxl, unsigned ny, RowDst dst,
+                                    const cd *__restrict__ tw)
+{
+    const unsigned row = blockIdx.x, k = blockIdx.y * blockDim.x + threadIdx.x;
+    if (row >= nxl || k > ny / 2) return;
+    const double *x = V + (unsigned long long) row * n_col;
+    double re = 0.0, im = 0.0;
+    unsigned idx = 0; // (j * k) mod ny, updated incrementally
+    for (unsigned j = 0; j < ny; ++j) {
+        const cd w = ldtw(tw, idx);
+        re += x[j] * w.x;
+        im += x[j] * w.y;
+        idx += k;
+        if (idx >= ny) idx -= ny;
+    }
+    if (k == 0 || 2 * k == ny) im = 0.0;
+    *rowdst_ptr(dst, row, k) = make_double2(re, im);
+}
+// grid = (ntiles * CW, ceil(nx/128)): one thread per (kx, local column)
+__global__ void cols_generic_kernel(InterView in, ColDst out, unsigned nx, const cd *__restrict__ tw)
+{
+    const unsigned kx = blockIdx.y * blockDim.x + threadIdx.x, kl = blockIdx.x;
+    if (kx >= nx || kl >= out.w) return;
+    const unsigned ct = kl / CW, c = kl % CW;
+    double re = 0.0, im = 0.0;
+    unsigned idx = 0;
+    for (unsigned x = 0; x < nx; ++x) {
+        const cd y = *inter_ptr(in, x, ct, c);
+        const cd w = ldtw(tw, idx);
+        re += y.x * w.x - y.y * w.y;
+        im += y.x * w.y + y.y * w.x;
+        idx += kx;
+        if (idx >= nx) idx -= nx;
+    }
+    *coldst_ptr(out, kx, kl) = make_double2(re, im);
+}
+
 // row-major [n][width] complex -> column-tiled I[ct][x][c] (one rank); test / adapter entry points only
 __global__ void tile_kernel(const cd *__restrict__ A, cd *__restrict__ I, unsigned n, unsigned width)
 {

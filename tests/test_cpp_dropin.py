@@ -70,6 +70,9 @@ def test_example_cli_csv_schema(cpp_bins, oracle, tmp_path):
     f = lines[1].split(";")
     assert f[1:5] == ["64", "128", "estimate", "par"] and len(f) == 15
     assert "FFTW r2c 1D plan:" in (tmp_path / "plans" / "plan_hpx_shared_loop.txt").read_text()
+    # the reference's default size (8 x 14) runs too
+    r2 = run([os.path.join(cpp_bins, "hpxfft_shared_loop"), "--result=1"], cwd=tmp_path)
+    assert r2.returncode == 0 and "(728 0) (-56 245.352)" in r2.stdout, r2.stdout + r2.stderr
     # --result prints the spectrum as "(re im)" pairs: row 0 of the ramp against the closed form
     row0 = [ln for ln in r.stdout.splitlines() if ln.startswith("(")][0]
     vals = np.array([float(t) for t in row0.replace("(", " ").replace(")", " ").split()])

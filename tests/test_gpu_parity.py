@@ -86,6 +86,19 @@ def test_small_pow2_sweep(pkg, oracle, nx, ny):
     assert oracle.rel_l2(got, ref) <= TOL
 
 
+@pytest.mark.parametrize("nx,ny", [(8, 14), (6, 10), (12, 30), (10, 16), (16, 18), (100, 200), (3, 2), (7, 1022), (1000, 64)])
+def test_generic_lengths(pkg, oracle, nx, ny):
+    """Lengths that are not powers of two (FFTW accepts any n; 8 x 14 is the reference example's default,
+    examples/hpxfft/shared_loop_2d.cpp:142-143) go through the direct-DFT kernels."""
+    a = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=7)
+    got, _ = shared_fft(pkg, a)
+    assert oracle.rel_l2(got, oracle.fft_2d_r2c_longdouble(a)) <= TOL
+    if (nx, ny) == (8, 14):
+        r = oracle.make_input(8, 14, oracle.PATTERN_RAMP)
+        z, _ = shared_fft(pkg, r)
+        assert z[0, 0] == 728.0 and abs(z[0, 2] + 56) < 1e-10 and abs(z[0, 3] - 245.352031) < 1e-5   # SURVEY appendix A
+
+
 def test_x_dependence_is_real(pkg, oracle):
     # the reference's tests only ever feed x-constant rows; a delta in x must produce the right phase ramp
     nx, ny = 64, 32
