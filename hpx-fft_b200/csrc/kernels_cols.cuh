@@ -315,32 +315,35 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
 
     // Thread 0 runs a two-deep claim queue so that neither the claim atomic nor the dependency poll
     // of the next tile sits on the critical path: both are issued while the current tile is computed.
+    // Two CTA barriers per tile: the one between the Stockham passes, and one at the end of the tile that
+    // simultaneously (i) orders this tile's stores before its completion signal, (ii) frees the tile buffer
+    // and (iii) publishes the next tile id that thread 0 wrote just before it.
+    __shared__ unsigned s_ready;
     unsigned t_cur = 0, t_next = 0, dep_seen = 0, dep_target = 0;
     const unsigned *dep_ptr = nullptr;
     if (threadIdx.x == 0) {
         t_cur = claim_tile(ctl.counter);
         t_next = claim_tile(ctl.counter);
         dep_ptr = dep_of(t_cur, dep_target);
-        dep_seen = 0;
+        if (dep_ptr)
+            while (ld_acquire_u32(dep_ptr) < dep_target) __nanosleep(64);
+        s_tile = t_cur;
+        s_ready = 1u;
     }
+    __syncthreads();
     for (;;) {
-        unsigned t_nn = 0, next_seen = 0, next_target = 0;
-        const unsigned *next_ptr = nullptr;
-        if (threadIdx.x == 0) {
-            if (dep_ptr && dep_seen < dep_target)
-                while (ld_acquire_u32(dep_ptr) < dep_target) __nanosleep(64);
-            s_tile = t_cur;
-        }
-        __syncthreads();
         const unsigned t = s_tile;
         if (t >= total) break;
+        unsigned t_nn = 0, next_seen = 0, next_target = 0;
+        const unsigned *next_ptr = nullptr;
         if (threadIdx.x == 0) {
             t_nn = claim_tile(ctl.counter);                 // consumed at the end of this iteration
             next_ptr = dep_of(t_next, next_target);
             if (next_ptr) next_seen = ld_acquire_u32(next_ptr); // early poll of the next tile's dependency
         }
         const unsigned g = t / PER_GROUP, r = t - g * PER_GROUP;
-        bool did = false;
+        unsigned *done = nullptr;
+        bool synced = false; // did every thread pass a CTA barrier since it read s_tile?
         if (r < (unsigned) N2) {
             // level A: tile x2 = r of strip g
             if (g < ntiles) {
@@ -350,8 +353,8 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
                 auto ld = [&](int i, int c) -> cd { return ld_stream(inter_ptr(in, (unsigned) i * N2 + x2, ct, (unsigned) c)); };
                 auto st = [&](int k1, int c, cd val) { st_cg(Sct + ((unsigned long long) k1 * N2 + x2) * CW + c, cmul(val, wil[k1])); };
                 tile_fft<N1>(smem, ptw1, ld, st);
-                cta_signal<0>(ctl.doneA + g);
-                did = true;
+                done = ctl.doneA + g;
+                synced = col_npass(N1) >= 2;
             }
         } else if (g >= ctl.lag) {
             // level B: tile k1 = r - N2 of strip g - lag
@@ -363,21 +366,38 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
                 if (kl < out.w) st_stream(coldst_ptr(out, k1 + (unsigned) N1 * (unsigned) k2, kl), val);
             };
             tile_fft<N2>(smem, ptw2, ld, st);
+            synced = col_npass(N2) >= 2;
+            if (!synced) {
+                __syncthreads(); // single-pass tile: no internal barrier, but the discard below needs one
+                synced = true;
+            }
             if (ctl.discard) {
-                // every thread's loads of this tile have been consumed (two barriers ago): retire the lines
+                // every thread's loads of this tile have been consumed (one barrier ago): retire the lines
                 for (int ln = threadIdx.x; ln < N2 * CW * (int) sizeof(cd) / 128; ln += NT)
                     l2_discard_line(reinterpret_cast<const char *>(Sk) + (size_t) ln * 128);
             }
-            cta_signal<0>(ctl.doneB + sl);
-            did = true;
+            done = ctl.doneB + sl;
         }
-        if (!did) __syncthreads(); // keep s_tile stable until every thread has read it
+        if (!synced) __syncthreads(); // skipped / single-pass tile: everybody has read s_tile before it changes
+        // publish the next tile; if its dependency is not known to be satisfied yet, say so and take the
+        // slow path below -- thread 0 must never spin while it still owes this tile's completion signal
+        if (threadIdx.x == 0) {
+            s_tile = t_next;
+            s_ready = (!next_ptr || next_seen >= next_target) ? 1u : 0u;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && done) {
+            __threadfence();
+            atomicAdd(done, 1u);
+        }
+        if (!s_ready) {
+            if (threadIdx.x == 0)
+                while (ld_acquire_u32(next_ptr) < next_target) __nanosleep(64);
+            __syncthreads();
+        }
         if (threadIdx.x == 0) {
             t_cur = t_next;
             t_next = t_nn;
-            dep_ptr = next_ptr;
-            dep_seen = next_seen;
-            dep_target = next_target;
         }
     }
 }
