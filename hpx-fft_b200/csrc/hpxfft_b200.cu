@@ -491,6 +491,16 @@ void fill_coldst(const hpxfft_b200_plan *p, ColDst &d)
     }
 }
 
+bool a2a_stepwise()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HPXFFT_B200_A2A_STEPWISE");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 int barrier_on_stream(hpxfft_b200_plan *p)
 {
     NC(g_nccl.AllReduce(p->d_barrier, p->d_barrier, 1, ncclInt, ncclSum, p->comm, p->stream));
@@ -505,13 +515,18 @@ int exchange1(hpxfft_b200_plan *p)
     for (int q = 0; q < P; ++q) soff[q + 1] = soff[q] + (unsigned long long) p->ntiles_of[q] * p->nxl * CW;
     const unsigned long long rblk = (unsigned long long) p->ntiles * p->nxl * CW; // what every peer sends me
     if (p->mode == MODE_ALL_TO_ALL) {
-        NC(g_nccl.GroupStart());
+        // rotation schedule: step s pairs every rank with (me+s) / (me-s).  Either all P-1 steps in one NCCL
+        // group (default) or one group per step (HPXFFT_B200_A2A_STEPWISE=1), which keeps each NVLink
+        // transfer at full per-pair channel count when P is large.
+        if (!a2a_stepwise()) NC(g_nccl.GroupStart());
         for (int s = 1; s < P; ++s) {
             const int to = (me + s) % P, from = (me - s + P) % P;
+            if (a2a_stepwise()) NC(g_nccl.GroupStart());
             NC(g_nccl.Send(p->bufA + soff[to], (soff[to + 1] - soff[to]) * 2, ncclDouble, to, p->comm, p->stream));
             NC(g_nccl.Recv(p->bufB + (unsigned long long) from * rblk, rblk * 2, ncclDouble, from, p->comm, p->stream));
+            if (a2a_stepwise()) NC(g_nccl.GroupEnd());
         }
-        NC(g_nccl.GroupEnd());
+        if (!a2a_stepwise()) NC(g_nccl.GroupEnd());
     } else { // scatter: one rooted scatter per locality, all in flight together like the reference's
              // asynchronous scatter_to / scatter_from futures (core/src/distributed/loop.cpp:158-167)
         NC(g_nccl.GroupStart());
@@ -535,14 +550,16 @@ int exchange2(hpxfft_b200_plan *p)
     const int P = p->P, me = p->rank;
     const unsigned long long sblk = (unsigned long long) p->nxl * p->w;
     if (p->mode == MODE_ALL_TO_ALL) {
-        NC(g_nccl.GroupStart());
+        if (!a2a_stepwise()) NC(g_nccl.GroupStart());
         for (int s = 1; s < P; ++s) {
             const int to = (me + s) % P, from = (me - s + P) % P;
+            if (a2a_stepwise()) NC(g_nccl.GroupStart());
             NC(g_nccl.Send(p->bufA + (unsigned long long) to * sblk, sblk * 2, ncclDouble, to, p->comm, p->stream));
             NC(g_nccl.Recv(p->bufB + (unsigned long long) p->nxl * p->c0_of[from], (unsigned long long) p->nxl * p->w_of[from] * 2,
                         ncclDouble, from, p->comm, p->stream));
+            if (a2a_stepwise()) NC(g_nccl.GroupEnd());
         }
-        NC(g_nccl.GroupEnd());
+        if (!a2a_stepwise()) NC(g_nccl.GroupEnd());
     } else {
         NC(g_nccl.GroupStart());
         for (int root = 0; root < P; ++root) {
