@@ -48,6 +48,20 @@ def algorithmic_bytes(nx: int, ny: int) -> dict:
     return {"rows": 8.0 * nx * ny + 16.0 * nx * cy, "cols": 32.0 * nx * cy, "total": 8.0 * nx * ny + 48.0 * nx * cy}
 
 
+def ncu_traffic(kernel: str, nx: int, ny: int, world: int):
+    """dram__bytes_read + dram__bytes_write per launch of `kernel` from the committed ncu --set full capture
+    (profiles/ncu_traffic.json), or None when no capture exists for this workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        if world != 1 or t.get("workload") != f"{nx}x{ny}":
+            return None
+        k = t["kernels"][kernel]
+        return k["dram_bytes_read"] + k["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def measured_peaks() -> tuple[float, str]:
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -253,6 +267,8 @@ def run_ours(args) -> dict | None:
         peak, how = measured_peaks()
         kernels = {"rows_r2c": (meas["rows_kernel"], ab["rows"] / world),
                    "cols_c2c": (meas["cols_kernel"], ab["cols"] / world)}
+        per_kernel = {k: {"ms": v[0] * 1e3, "algorithmic_bytes": v[1], "achieved_gbs": (v[1] / v[0] / 1e9 if v[0] > 0 else 0.0),
+                          "traffic": ncu_traffic(k, nx, ny, world)} for k, v in kernels.items()}
         dom = max(kernels, key=lambda k: kernels[k][0])
         dsec, dbytes = kernels[dom]
         achieved = dbytes / dsec / 1e9 if dsec > 0 else 0.0
@@ -271,8 +287,9 @@ def run_ours(args) -> dict | None:
             "gpu_launches": launches,
             "phases_ms": {k: meas[k] * 1e3 for k in meas if k != "timer_samples"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({how})", "traffic": None,
-                         "algorithmic_bytes_per_launch": dbytes, "avg_kernel_ms": dsec * 1e3,
+                         "frac": achieved / peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({how})",
+                         "traffic": ncu_traffic(dom, nx, ny, world), "traffic_source": "profiles/ncu_traffic.json (ncu --set full, per launch)",
+                         "algorithmic_bytes_per_launch": dbytes, "avg_kernel_ms": dsec * 1e3, "per_kernel": per_kernel,
                          "whole_transform": {"algorithmic_bytes": ab["total"] / world, "compute_ms": compute_sec * 1e3,
                                              "achieved": ab["total"] / world / compute_sec / 1e9 if compute_sec > 0 else 0.0,
                                              "frac": ab["total"] / world / compute_sec / 1e9 / peak if compute_sec > 0 else 0.0}},
