@@ -6,10 +6,11 @@
 // the result is written directly in the column-tiled intermediate layout (layout.cuh).
 //
 // Algorithm: z[j] = x[2j] + i x[2j+1] (a row of ny doubles *is* ny/2 double2), length-m complex
-// Stockham FFT (m = ny/2) with the whole pencil resident in shared memory, first pass fed straight
-// from coalesced 16-byte global loads, last pass radix-16 on *pairs* of butterflies (columns j and
-// PP-j) so that the Hermitian split X[k] = E[k] - i w_n^k O[k] finds both Z[k] and Z[m-k] in the
-// same thread's registers and the result goes to global memory without another exchange.
+// Stockham FFT (m = ny/2) with the whole pencil resident in shared memory; the raw row is staged into
+// the pencil buffer by cp.async while the PREVIOUS row finishes in registers, the last pass is radix-16
+// on *pairs* of butterflies (columns j and PP-j) so that the Hermitian split X[k] = E[k] - i w_n^k O[k]
+// finds both Z[k] and Z[m-k] in the same thread's registers and the result goes to global memory
+// without another exchange.  Twiddles come from shared-memory tables built once per persistent CTA.
 #pragma once
 #include "layout.cuh"
 
