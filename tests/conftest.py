@@ -12,6 +12,10 @@ import __graft_entry__ as entry  # noqa: E402
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build them once, in-tree
+    lib = os.path.join(ROOT, "hpx-fft_b200", "libhpxfft_b200.so")
+    if not os.path.exists(lib):
+        entry.build()
 
 
 @pytest.fixture(scope="session")
