@@ -29,16 +29,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: str = LIB) -> str:
+    """`defines` / `out` produce variant libraries for A/B runs (selected with HPXFFT_B200_LIB)."""
+    if not force and out == LIB and not needs_build():
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+           "-Xcompiler", "-fPIC", "-shared", "-o", out] + [f"-D{d}" for d in defines] + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True, cwd=CSRC)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

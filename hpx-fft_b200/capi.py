@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhpxfft_b200.so")
+LIB_PATH = os.environ.get("HPXFFT_B200_LIB") or os.path.join(HERE, "libhpxfft_b200.so")  # override: A/B builds
 
 OK, EINVAL, EPLANFLAG, ECOMMFLAG, ECUDA, ENCCL, ESTATE = 0, -1, -2, -3, -4, -5, -6
 UNIQUE_ID_BYTES = 128

@@ -268,15 +268,18 @@ template <int N1, int N2> __host__ __device__ constexpr size_t fused_tile_bytes(
 {
     return col_tile_bytes(N1) > col_tile_bytes(N2) ? col_tile_bytes(N1) : col_tile_bytes(N2);
 }
-// tile | pass twiddles N1 | pass twiddles N2 | inter-level row
+// tile | pass twiddles N1 | pass twiddles N2 (shared with N1's when N1 == N2: same contents) | inter-level row
 template <int N1, int N2> __host__ __device__ constexpr size_t fused_smem_bytes()
 {
-    return fused_tile_bytes<N1, N2>() + col_tw_bytes(N1) + col_tw_bytes(N2) + N1 * sizeof(cd);
+    return fused_tile_bytes<N1, N2>() + col_tw_bytes(N1) + (N1 == N2 ? 0 : col_tw_bytes(N2)) + N1 * sizeof(cd);
 }
 // resident CTAs per SM the register allocator is asked to make room for
+#ifndef HPXFFT_B200_FUSED_MINBLOCKS
+#define HPXFFT_B200_FUSED_MINBLOCKS 5
+#endif
 template <int N1, int N2> __host__ __device__ constexpr int fused_min_blocks()
 {
-    return fused_threads<N1, N2>() <= 128 ? 5 : (fused_threads<N1, N2>() <= 256 ? 2 : 1);
+    return fused_threads<N1, N2>() <= 128 ? HPXFFT_B200_FUSED_MINBLOCKS : (fused_threads<N1, N2>() <= 256 ? 2 : 1);
 }
 
 template <int N1, int N2>
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
     constexpr int NT = fused_threads<N1, N2>();
     cd *smem = reinterpret_cast<cd *>(smem_raw);
     cd *ptw1 = reinterpret_cast<cd *>(smem_raw + fused_tile_bytes<N1, N2>());
-    cd *ptw2 = ptw1 + col_tw_entries(N1);
+    cd *ptw2 = N1 == N2 ? ptw1 : ptw1 + col_tw_entries(N1);
     cd *wil = ptw2 + col_tw_entries(N2);
     __shared__ unsigned s_tile;
     constexpr unsigned PER_GROUP = N1 + N2;
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
     const unsigned long long slot_elems = (unsigned long long) N1 * N2 * CW;
 
     fill_pass_twiddles<N1>(ptw1, tw, (unsigned) N2, (int) threadIdx.x, NT);
-    fill_pass_twiddles<N2>(ptw2, tw, (unsigned) N1, (int) threadIdx.x, NT);
+    if (N1 != N2) fill_pass_twiddles<N2>(ptw2, tw, (unsigned) N1, (int) threadIdx.x, NT);
 
     // dependency of tile t: (counter address, target) -- nullptr when there is none
     auto dep_of = [&](unsigned t, unsigned &target) -> const unsigned * {
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
     // simultaneously (i) orders this tile's stores before its completion signal, (ii) frees the tile buffer
     // and (iii) publishes the next tile id that thread 0 wrote just before it.
     __shared__ unsigned s_ready;
-    unsigned t_cur = 0, t_next = 0, dep_seen = 0, dep_target = 0;
+    unsigned t_cur = 0, t_next = 0, dep_target = 0;
     const unsigned *dep_ptr = nullptr;
     if (threadIdx.x == 0) {
         t_cur = claim_tile(ctl.counter);
@@ -467,7 +470,8 @@ __global__ void __launch_bounds__(tma_threads<N1, N2>(), tma_min_blocks<N1, N2>(
     cols_fused_tma_kernel(InterView in, cd *__restrict__ S, ColDst out, const cd *__restrict__ tw, const cd *__restrict__ W2, unsigned ntiles,
                           FusedCtl ctl)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw_tma[];
+    unsigned char *smem_raw = smem_raw_tma;
     constexpr int NCT = tma_consumer_threads<N1, N2>();
     constexpr unsigned PER_GROUP = N1 + N2;
     constexpr unsigned END = 0xffffffffu;
