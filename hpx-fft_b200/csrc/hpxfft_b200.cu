@@ -991,9 +991,8 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         p->n2 = 1;
     }
 
-    cudaEvent_t t0, t1;
-    CU(cudaEventCreate(&t0));
-    CU(cudaEventCreate(&t1));
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (cudaEventCreate(&t0) != cudaSuccess || cudaEventCreate(&t1) != cudaSuccess) return bail(fail(HPXFFT_B200_ECUDA, "event create failed"));
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(HPXFFT_B200_ECUDA, "stream create failed"));
     p->evs.assign((size_t) hpxfft_b200_plan::EV_SETS * hpxfft_b200_plan::EV_PER_SET, nullptr);
     for (auto &e : p->evs)
