@@ -129,6 +129,8 @@ def dist_setup(n_gpus: int):
     if world == 1:
         return 0, 1, 0, None
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    # keep stdout to the one JSON line: NCCL's "NCCL version ..." banner goes to a file instead
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/hpxfft_b200_nccl_%h_%p.log")
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
