@@ -24,6 +24,13 @@ def test_row_kernel_paired_last_pass_and_hermitian_split(m, prefix):   # kernels
     assert np.abs(mk.r2c_row_model(xr, prefix) - np.fft.rfft(xr)).max() < 1e-11 * m
 
 
+@pytest.mark.parametrize("m,prefix", [(256, [4, 8]), (1024, [16, 8]), (2048, [16, 16])])
+def test_paired_radix8_last_pass(m, prefix):
+    """The 16-points-per-thread row plan (paired radix-8 last pass) planned for the 512-thread row kernel."""
+    xr = np.random.default_rng(m + 1).standard_normal(2 * m)
+    assert np.abs(mk.r2c_row_model(xr, prefix, RL=8) - np.fft.rfft(xr)).max() < 1e-11 * m
+
+
 @pytest.mark.parametrize("n1,n2,p1,p2", [(16, 16, [16], [16]), (32, 16, [8, 4], [16]), (32, 32, [8, 4], [8, 4])])
 def test_four_step_column_fft(n1, n2, p1, p2):             # kernels_cols.cuh: level A / level B
     rng = np.random.default_rng(n1 * n2)
