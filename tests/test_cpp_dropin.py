@@ -28,6 +28,20 @@ def test_cpp_headers_compile_and_vector_2d(cpp_bins):
     assert r.returncode == 0 and "test_vector_2d ok" in r.stdout, r.stderr
 
 
+@pytest.mark.parametrize("world", [1, 3])
+def test_cpp_bootstrap_rendezvous(cpp_bins, world, tmp_path):
+    """world_size-3 exchange through the shared-directory rendezvous (no HPX, no GPU)."""
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_PORT="4712",
+                   HPXFFT_B200_RENDEZVOUS=str(tmp_path))
+        procs.append(subprocess.Popen([os.path.join(cpp_bins, "test_bootstrap")], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "test_bootstrap ok" in o, o
+
+
 @pytest.mark.gpu
 def test_cpp_shared_loop_golden(cpp_bins):
     r = run([os.path.join(cpp_bins, "test_shared_loop")])
