@@ -212,7 +212,7 @@ template <int M, int C, bool FAST> int launch_rows_big_t(const hpxfft_b200_plan 
     CU(cudaGetLastError());
     if (C > 2) {
         const unsigned m = (unsigned) M * C;
-        herm_split_kernel<<<dim3((m / 2 + 1 + 255) / 256, nrows), 256, 0, p->stream>>>(p->zraw, m, nrows, dst, p->tw_row);
+        herm_split_kernel<<<dim3(nrows, (m / 2 + 1 + 255) / 256), 256, 0, p->stream>>>(p->zraw, m, nrows, dst, p->tw_row);
         CU(cudaGetLastError());
     }
     return 0;

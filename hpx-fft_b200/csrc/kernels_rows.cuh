@@ -303,11 +303,11 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
 }
 
 // Hermitian split as a separate pass (rows longer than 2*8192 complex): zraw[row][k], k < m  ->  X[k], k <= m.
-// grid = (ceil((m/2+1)/256), nxl)
+// grid = (nxl, ceil((m/2+1)/256))  -- rows on grid.x: a slab may have more than 65535 rows
 __global__ void herm_split_kernel(const cd *__restrict__ zraw, unsigned m, unsigned nxl, RowDst dst, const cd *__restrict__ tw)
 {
-    const unsigned row = blockIdx.y;
-    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned row = blockIdx.x;
+    const unsigned k = blockIdx.y * blockDim.x + threadIdx.x;
     if (row >= nxl || k > m / 2) return;
     const cd *zr = zraw + (unsigned long long) row * m;
     if (k == 0) {
