@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhpxfft_b200.so")
 SOURCES = ["hpxfft_b200.cu"]
-HEADERS = ["fft_device.cuh", "layout.cuh", "kernels_rows.cuh", "kernels_cols.cuh", "kernels_misc.cuh",
+HEADERS = ["fft_device.cuh", "layout.cuh", "kernels_rows.cuh", "kernels_rows16.cuh", "kernels_cols.cuh", "kernels_misc.cuh",
            os.path.join("..", "..", "include", "hpxfft_b200.h")]
 
 

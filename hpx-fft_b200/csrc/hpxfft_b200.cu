@@ -9,6 +9,7 @@
 #include "kernels_cols.cuh"
 #include "kernels_misc.cuh"
 #include "kernels_rows.cuh"
+#include "kernels_rows16.cuh"
 
 #include <nccl.h>  // types only: the library is dlopen'ed lazily (see NcclApi) so that a host process
                    // that already carries its own libnccl.so.2 (e.g. PyTorch's bundled one) is reused
@@ -227,6 +228,33 @@ template <int M, int C = 1> int launch_rows_big(const hpxfft_b200_plan *p, const
     return launch_rows_big_t<M, C, false>(p, dst, nrows, V, pitch);
 }
 
+// EXPERIMENTAL 512-thread row kernel (kernels_rows16.cuh), opt-in with HPXFFT_B200_ROWS16=1
+bool rows16_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HPXFFT_B200_ROWS16");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+template <bool FAST> int launch_rows16_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+{
+    static int configured = -1;
+    if (configured != p->device) {
+        if (int rc = set_smem(rows16_r2c_kernel<FAST>, rows16::SMEM)) return rc;
+        configured = p->device;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    sms -= p->sm_reserve;
+    const unsigned grid = nrows < (unsigned) sms ? nrows : (unsigned) sms;
+    rows16_r2c_kernel<FAST><<<grid, rows16::T, rows16::SMEM, p->stream>>>(V, pitch, nrows, dst, p->tw_row);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 template <int M> int launch_rows_tiny(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
 {
     const unsigned block = 128, grid = (nrows + block - 1) / block;
@@ -257,7 +285,9 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
     case 1024: return launch_rows_big<1024>(p, dst, nrows, V, pitch);
     case 2048: return launch_rows_big<2048>(p, dst, nrows, V, pitch);
     case 4096: return launch_rows_big<4096>(p, dst, nrows, V, pitch);
-    case 8192: return launch_rows_big<8192>(p, dst, nrows, V, pitch);
+    case 8192:
+        if (rows16_enabled()) return dst.P == 1 ? launch_rows16_t<true>(p, dst, nrows, V, pitch) : launch_rows16_t<false>(p, dst, nrows, V, pitch);
+        return launch_rows_big<8192>(p, dst, nrows, V, pitch);
     case 16384: return launch_rows_big<8192, 2>(p, dst, nrows, V, pitch);
     case 32768: return launch_rows_big<8192, 4>(p, dst, nrows, V, pitch);
     case 65536: return launch_rows_big<8192, 8>(p, dst, nrows, V, pitch);
