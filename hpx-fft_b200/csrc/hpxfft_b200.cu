@@ -158,6 +158,9 @@ struct hpxfft_b200_plan {
     cd *tw_row = nullptr, *tw_col = nullptr;
     cd *tw_il = nullptr;   // inter-level twiddles of the four-step column FFT, [x2][k1] = w_nx^(k1*x2)
     size_t bytesA = 0, bytesB = 0, bytesS = 0;
+    // Experimental (single rank only): extra rows of padding between the column tiles of I, so that the tile
+    // stride is not a power of two (suspected DRAM channel aliasing of the 256-byte segment traffic).
+    size_t tile_pad_rows = 0;
     // p2p
     std::vector<void *> peerI, peerV;
     bool ipc_imported = false;
@@ -481,7 +484,7 @@ int parse_comm_flag(const char *f, int *mode)
 
 int fill_rowdst(const hpxfft_b200_plan *p, RowDst &d)
 {
-    d.tile_stride = (unsigned long long) p->nxl * CW;
+    d.tile_stride = (unsigned long long) (p->nxl + p->tile_pad_rows) * CW;
     d.cy = (unsigned) p->cy;
     d.wq0 = p->wq0;
     d.P = (unsigned) p->P;
@@ -783,8 +786,8 @@ int enqueue_transform(hpxfft_b200_plan *p)
     iv.base = p->bufB;
     iv.nxl = (unsigned) p->nxl;
     iv.shift = pow2_shift(iv.nxl);
-    iv.tile_stride = (unsigned long long) p->nxl * CW;
-    iv.rank_stride = (unsigned long long) p->ntiles * p->nxl * CW;
+    iv.tile_stride = (unsigned long long) (p->nxl + p->tile_pad_rows) * CW;
+    iv.rank_stride = (unsigned long long) p->ntiles * (p->nxl + p->tile_pad_rows) * CW;
 
     cudaEvent_t *ev = p->evs.data() + (size_t) (p->nrec % hpxfft_b200_plan::EV_SETS) * hpxfft_b200_plan::EV_PER_SET;
     p->nrec += 1;
@@ -1033,7 +1036,10 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
 
     // buffers
     const size_t bytesV = p->nxl * p->n_col * sizeof(double);
-    p->bytesB = (size_t) p->ntiles * p->nx * CW * sizeof(cd); // I: [r][ct][j][c], also >= nxl*cy for exchange #2
+    if (nranks == 1) {
+        if (const char *e = getenv("HPXFFT_B200_TILE_PAD")) { int v = atoi(e); if (v > 0 && v <= 4096) p->tile_pad_rows = (size_t) v; }
+    }
+    p->bytesB = (size_t) p->ntiles * (p->nx + p->tile_pad_rows) * CW * sizeof(cd); // I: [r][ct][j][c], also >= nxl*cy for exchange #2
     if (p->bytesB < p->nxl * p->cy * sizeof(cd)) p->bytesB = p->nxl * p->cy * sizeof(cd);
     p->bytesS = p->two_level ? (size_t) p->ntiles * p->nx * CW * sizeof(cd) : 0;
     if (p->two_level) {
