@@ -1,17 +1,23 @@
-"""Builds libhpxfft_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+"""Builds libhpxfft_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo).
+The translation units are compiled in parallel and linked into one shared library."""
 from __future__ import annotations
 
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhpxfft_b200.so")
-SOURCES = ["hpxfft_b200.cu"]
-HEADERS = ["fft_device.cuh", "layout.cuh", "kernels_rows.cuh", "kernels_rows16.cuh", "kernels_cols.cuh", "kernels_misc.cuh",
-           os.path.join("..", "..", "include", "hpxfft_b200.h")]
+# (source, extra defines, object suffix)
+UNITS = [("common.cu", (), ""), ("plan.cu", (), ""), ("launch_rows.cu", (), ""), ("launch_cols.cu", (), ""), ("launch_misc.cu", (), ""),
+         ("launch_generic.cu", (), "")] + \
+        [("launch_fused.cu", (f"HPXFFT_B200_FUSED_GROUP={g}",), f"_g{g}") for g in range(4)]
+HEADERS = ["fft_device.cuh", "layout.cuh", "kernels_rows.cuh", "kernels_cols.cuh", "kernels_misc.cuh", "kernels_generic.cuh",
+           "internal.h", "launch_util.h", os.path.join("..", "..", "include", "hpxfft_b200.h")]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def _nvcc() -> str:
@@ -21,11 +27,15 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def _units():
+    return [u for u in UNITS if os.path.exists(os.path.join(CSRC, u[0]))]
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, s) for s in [u[0] for u in UNITS] + HEADERS]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -33,15 +43,33 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: 
     """`defines` / `out` produce variant libraries for A/B runs (selected with HPXFFT_B200_LIB)."""
     if not force and out == LIB and not needs_build():
         return LIB
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", out] + [f"-D{d}" for d in defines] + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True, cwd=CSRC)
+    tag = "" if out == LIB else "_" + os.path.splitext(os.path.basename(out))[0]
+    objdir = os.path.join(HERE, "build" + tag)
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS if os.path.exists(os.path.join(CSRC, h)))
+
+    def compile_one(unit):
+        src, defs, suffix = unit
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + suffix + ".o")
+        srcp = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(hdr_t, os.path.getmtime(srcp)):
+            return obj
+        cmd = [nvcc] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-c", "-o", obj] + \
+              [f"-D{d}" for d in tuple(defines) + tuple(defs)] + [srcp]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True, cwd=CSRC)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, _units()))
+    subprocess.run([nvcc] + ARCH + ["-shared", "-o", out] + objs + ["-ldl"], check=True, cwd=CSRC)
     return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    outs = [a[len("--out="):] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else LIB))

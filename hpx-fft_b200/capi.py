@@ -24,6 +24,11 @@ PROTOTYPES = {
     "hpxfft_b200_ipc_count": (C.c_int, [C.c_void_p]),
     "hpxfft_b200_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hpxfft_b200_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hpxfft_b200_transport": (C.c_char_p, [C.c_void_p]),
+    "hpxfft_b200_bind_host_to_device": (C.c_int, [C.c_int]),
+    "hpxfft_b200_download_tile": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "hpxfft_b200_bench_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "hpxfft_b200_c2c_cols_variant": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int]),
     "hpxfft_b200_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hpxfft_b200_download": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hpxfft_b200_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64]),

@@ -13,14 +13,24 @@ typedef double2 cd;
 
 __device__ __forceinline__ cd cadd(cd a, cd b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ cd csub(cd a, cd b) { return make_double2(a.x - b.x, a.y - b.y); }
+// Diagnostic builds (never shipped, see tools/diag_builds.sh): HPXFFT_B200_DIAG_NOMATH removes the FP64 work so that
+// a kernel's memory / shared-memory / barrier skeleton can be timed alone (results are garbage).
 __device__ __forceinline__ cd cmul(cd a, cd b)
 {
+#ifdef HPXFFT_B200_DIAG_NOMATH
+    return a;
+#else
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+#endif
 }
 // a * conj(b)
 __device__ __forceinline__ cd cmulc(cd a, cd b)
 {
+#ifdef HPXFFT_B200_DIAG_NOMATH
+    return a;
+#else
     return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+#endif
 }
 __device__ __forceinline__ cd cconj(cd a) { return make_double2(a.x, -a.y); }
 
@@ -69,6 +79,9 @@ __device__ __forceinline__ cd mulw32(cd a, int idx)
                               0.38268343236508977173,
                               0.19509032201612826785};
     constexpr double R2 = 0.70710678118654752440;
+#ifdef HPXFFT_B200_DIAG_NOMATH
+    return a;
+#endif
     if (idx == 0) return a;
     if (idx == 8) return make_double2(a.y, -a.x);
     if (idx == 4) return make_double2(R2 * (a.x + a.y), R2 * (a.y - a.x));
@@ -84,6 +97,9 @@ __device__ __forceinline__ void fft_dif(cd (&v)[R])
 {
     static_assert(R >= 1 && R <= 32 && (R & (R - 1)) == 0, "radix must be a power of two <= 32");
     constexpr int L = ilog2(R);
+#ifdef HPXFFT_B200_DIAG_NOMATH
+    return;
+#endif
 #pragma unroll
     for (int s = 0; s < L; ++s) {
         const int h = (R / 2) >> s;

@@ -14,8 +14,7 @@
 //                    w_nx^(k1*x2), write scratch S[strip][k1][x2][c].  Level B: for every k1, FFT over x2
 //                    (contiguous in S), result row kx = k1 + n1*k2 goes straight to its final position.
 //                    Run as two launches (cols_levelA/B_kernel, S = full array in HBM) or fused in one
-//                    persistent launch whose scratch ring stays in L2 (cols_fused_kernel and the
-//                    warp-specialised TMA-bulk/mbarrier variant cols_fused_tma_kernel).
+//                    persistent launch whose scratch ring stays in L2 (cols_fused_kernel).
 #pragma once
 #include "layout.cuh"
 
@@ -350,7 +349,11 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
         if (r < (unsigned) N2) {
             // level A: tile x2 = r of strip g
             if (g < ntiles) {
+#ifdef HPXFFT_B200_DIAG_WRAP
+                const unsigned x2 = r, ct = (ctl.ct0 + g) & 1u;
+#else
                 const unsigned x2 = r, ct = ctl.ct0 + g;
+#endif
                 for (int i = threadIdx.x; i < N1; i += NT) wil[i] = ldtw(W2, x2 * (unsigned) N1 + (unsigned) i);
                 cd *Sct = S + (unsigned long long) (g % ctl.nslot) * slot_elems;
                 auto ld = [&](int i, int c) -> cd { return ld_stream(inter_ptr(in, (unsigned) i * N2 + x2, ct, (unsigned) c)); };
@@ -361,7 +364,11 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
             }
         } else if (g >= ctl.lag) {
             // level B: tile k1 = r - N2 of strip g - lag
+#ifdef HPXFFT_B200_DIAG_WRAP
+            const unsigned k1 = r - N2, sl = g - ctl.lag, ct = (ctl.ct0 + sl) & 1u;
+#else
             const unsigned k1 = r - N2, sl = g - ctl.lag, ct = ctl.ct0 + sl;
+#endif
             const cd *Sk = S + (unsigned long long) (sl % ctl.nslot) * slot_elems + (unsigned long long) k1 * N2 * CW;
             auto ld = [&](int i, int c) -> cd { return ld_cg(Sk + (unsigned) i * CW + c); };
             auto st = [&](int k2, int c, cd val) {
@@ -401,185 +408,6 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
         if (threadIdx.x == 0) {
             t_cur = t_next;
             t_next = t_nn;
-        }
-    }
-}
-
-// ---- warp-specialised fused four-step: TMA bulk copies + mbarriers -------------------------------
-//
-// Same tile order, dependency counters and L2-resident scratch ring as cols_fused_kernel, but the tile
-// that a CTA will work on next is already being copied into a shared-memory staging buffer by a
-// dedicated producer warp (cp.async.bulk, completion on an mbarrier) while the consumer warps are
-// still computing the current tile.  The producer also owns the tile claim and the dependency wait,
-// so none of those latencies is seen by the math warps.  The copies land IN the tile buffer (no staging
-// copy, same shared-memory footprint as the plain kernel).  Level-B tiles are one contiguous 16*N2*CW-byte
-// bulk copy out of the scratch ring; level-A tiles are N1 copies of one CW*16-byte row segment each,
-// plus the N1*16-byte row of inter-level twiddles.
-namespace ptx {
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "MBAR_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MBAR_DONE_%=;\n"
-        "bra MBAR_WAIT_%=;\n"
-        "MBAR_DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-}  // namespace ptx
-
-template <int N1, int N2> __host__ __device__ constexpr int tma_consumer_threads() { return fused_threads<N1, N2>(); }
-template <int N1, int N2> __host__ __device__ constexpr int tma_threads() { return fused_threads<N1, N2>() + 32; }
-// tile (refilled in place by the producer) | pass twiddles N1 | pass twiddles N2 | inter-level rows (double-buffered)
-template <int N1, int N2> __host__ __device__ constexpr size_t tma_smem_bytes()
-{
-    return fused_tile_bytes<N1, N2>() + col_tw_bytes(N1) + col_tw_bytes(N2) + 2 * N1 * sizeof(cd);
-}
-template <int N1, int N2> __host__ __device__ constexpr int tma_min_blocks()
-{
-    return tma_threads<N1, N2>() <= 160 ? 4 : (tma_threads<N1, N2>() <= 288 ? 2 : 1);
-}
-
-template <int N1, int N2>
-__global__ void __launch_bounds__(tma_threads<N1, N2>(), tma_min_blocks<N1, N2>())
-    cols_fused_tma_kernel(InterView in, cd *__restrict__ S, ColDst out, const cd *__restrict__ tw, const cd *__restrict__ W2, unsigned ntiles,
-                          FusedCtl ctl)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw_tma[];
-    unsigned char *smem_raw = smem_raw_tma;
-    constexpr int NCT = tma_consumer_threads<N1, N2>();
-    constexpr unsigned PER_GROUP = N1 + N2;
-    constexpr unsigned END = 0xffffffffu;
-    // ONE buffer: the producer's bulk copies land where the consumers run the FFT.  The consumers arrive on
-    // empty_bar right after the last pass has read the tile, so the refill for tile i+1 overlaps the
-    // last-pass butterflies, twiddles and stores of tile i without costing any extra shared memory.
-    cd *tile = reinterpret_cast<cd *>(smem_raw);
-    cd *stage = tile;
-    cd *ptw1 = reinterpret_cast<cd *>(smem_raw + fused_tile_bytes<N1, N2>());
-    cd *ptw2 = ptw1 + col_tw_entries(N1);
-    cd *wil = ptw2 + col_tw_entries(N2); // [2][N1]
-    __shared__ __align__(8) unsigned long long full_bar, empty_bar;
-    __shared__ unsigned s_info;
-    const unsigned total = (ntiles + ctl.lag) * PER_GROUP;
-    const unsigned long long slot_elems = (unsigned long long) N1 * N2 * CW;
-
-    if (threadIdx.x == 0) {
-        ptx::mbar_init(&full_bar, 1);
-        ptx::mbar_init(&empty_bar, NCT);
-        ptx::fence_mbar_init();
-    }
-    if (threadIdx.x < NCT) {
-        fill_pass_twiddles<N1>(ptw1, tw, (unsigned) N2, (int) threadIdx.x, NCT);
-        fill_pass_twiddles<N2>(ptw2, tw, (unsigned) N1, (int) threadIdx.x, NCT);
-    }
-    __syncthreads();
-
-    if (threadIdx.x >= NCT) {
-        // ================= producer warp =================
-        const unsigned lane = threadIdx.x - NCT;
-        unsigned parity_e = 1; // the staging buffer starts out free
-        unsigned wsel = 0;     // inter-level twiddle buffer the next level-A tile will use
-        for (;;) {
-            // claim the next non-empty tile
-            unsigned t = 0, g = 0, r = 0;
-            bool isA = false;
-            for (;;) {
-                if (lane == 0) t = claim_tile(ctl.counter);
-                t = __shfl_sync(0xffffffffu, t, 0);
-                if (t >= total) break;
-                g = t / PER_GROUP;
-                r = t - g * PER_GROUP;
-                isA = r < (unsigned) N2;
-                if (isA ? (g < ntiles) : (g >= ctl.lag)) break;
-            }
-            if (t >= total) {
-                if (lane == 0) {
-                    ptx::mbar_wait(&empty_bar, parity_e);
-                    s_info = END;
-                    ptx::mbar_arrive(&full_bar);
-                }
-                break;
-            }
-            // dependency: level B needs its strip's level-A tiles; level A needs its scratch slot drained
-            if (lane == 0) {
-                if (isA) {
-                    if (g >= ctl.nslot)
-                        while (ld_acquire_u32(ctl.doneB + (g - ctl.nslot)) < (unsigned) N1) __nanosleep(64);
-                } else {
-                    while (ld_acquire_u32(ctl.doneA + (g - ctl.lag)) < (unsigned) N2) __nanosleep(64);
-                }
-                ptx::mbar_wait(&empty_bar, parity_e);
-                s_info = t;
-                ptx::mbar_arrive_expect_tx(&full_bar, (unsigned) (isA ? (N1 * CW + N1) * sizeof(cd) : N2 * CW * sizeof(cd)));
-            }
-            parity_e ^= 1u;
-            __syncwarp();
-            if (isA) {
-                const unsigned x2 = r, ct = ctl.ct0 + g;
-                for (unsigned i = lane; i < (unsigned) N1; i += 32)
-                    ptx::bulk_g2s(stage + i * CW, inter_ptr(in, i * N2 + x2, ct, 0u), CW * sizeof(cd), &full_bar);
-                if (lane == 0) ptx::bulk_g2s(wil + wsel * N1, W2 + (unsigned long long) x2 * N1, N1 * sizeof(cd), &full_bar);
-                wsel ^= 1u;
-            } else if (lane == 0) {
-                const unsigned k1 = r - N2, sl = g - ctl.lag;
-                const cd *Sk = S + (unsigned long long) (sl % ctl.nslot) * slot_elems + (unsigned long long) k1 * N2 * CW;
-                ptx::bulk_g2s(stage, Sk, (unsigned) (N2 * CW * sizeof(cd)), &full_bar);
-            }
-        }
-    } else {
-        // ================= consumer warps =================
-        unsigned parity_f = 0, wsel = 0;
-        auto release_stage = [&]() { ptx::mbar_arrive(&empty_bar); };   // tile buffer dead: producer may refill
-        auto inputs_read = [&]() { tile_barrier<NCT>(); };              // in-place first pass: all reads before any write
-        for (;;) {
-            ptx::mbar_wait(&full_bar, parity_f);
-            parity_f ^= 1u;
-            const unsigned t = s_info;
-            if (t == END) break;
-            const unsigned g = t / PER_GROUP, r = t - g * PER_GROUP;
-            auto ld = [&](int i, int c) -> cd { return stage[i * CW + c]; };
-            if (r < (unsigned) N2) {
-                const unsigned x2 = r;
-                const cd *w = wil + wsel * N1;
-                wsel ^= 1u;
-                cd *Sct = S + (unsigned long long) (g % ctl.nslot) * slot_elems;
-                auto st = [&](int k1, int c, cd val) { st_cg(Sct + ((unsigned long long) k1 * N2 + x2) * CW + c, cmul(val, w[k1])); };
-                tile_fft<N1, NCT>(tile, ptw1, ld, st, inputs_read, release_stage);
-                cta_signal<NCT>(ctl.doneA + g);
-            } else {
-                const unsigned k1 = r - N2, sl = g - ctl.lag, ct = ctl.ct0 + sl;
-                auto st = [&](int k2, int c, cd val) {
-                    const unsigned kl = ct * CW + c;
-                    if (kl < out.w) st_stream(coldst_ptr(out, k1 + (unsigned) N1 * (unsigned) k2, kl), val);
-                };
-                tile_fft<N2, NCT>(tile, ptw2, ld, st, inputs_read, release_stage);
-                cta_signal<NCT>(ctl.doneB + sl);
-            }
         }
     }
 }

@@ -58,12 +58,7 @@ __global__ void unpack_kernel(const cd *__restrict__ recv2, cd *__restrict__ V, 
     for (unsigned k = threadIdx.x; k < w; k += blockDim.x) st_stream(dst + k, ld_stream(src + k));
 }
 
-// chunked variant for the pipelined exchange #2: one dense [nxl][wc_q] block per source rank
-struct UnpackChunk {
-    unsigned long long src_off[MAXP]; // element offset of the block inside the receive buffer
-    unsigned dst_col[MAXP];           // first destination column in V
-    unsigned wc[MAXP];                // block width (0 = nothing from this rank)
-};
+// chunked variant for the pipelined exchange #2 (UnpackChunk: layout.cuh)
 // grid = (nxl, P)
 __global__ void unpack_chunk_kernel(const cd *__restrict__ recv, cd *__restrict__ V, unsigned cy, UnpackChunk u)
 {

@@ -41,6 +41,11 @@ template <int PS> __device__ __forceinline__ int rpad(int a) { return a + (a >> 
 // Hermitian split of one pair: a = Z[k], b = Z[m-k], w = w_n^k  ->  xk = X[k], xmk = X[m-k]
 __device__ __forceinline__ void herm_pair(cd a, cd b, cd w, cd &xk, cd &xmk)
 {
+#ifdef HPXFFT_B200_DIAG_NOMATH
+    xk = a;
+    xmk = b;
+    return;
+#endif
     const cd s = make_double2(a.x + b.x, a.y - b.y); // a + conj(b)
     const cd d = make_double2(a.x - b.x, a.y + b.y); // a - conj(b)
     const cd t = cmul(d, make_double2(0.5 * w.x, 0.5 * w.y));
@@ -78,6 +83,20 @@ __device__ __forceinline__ void cp_async16(cd *dst_smem, const cd *src_gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned) __cvta_generic_to_shared(dst_smem)), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Long rows (C > 1) cannot be staged (the pencil buffer only holds 1/C of a row): instead every CTA of the row pulls
+// its 1/C of the NEXT row into L2 while the current row finishes in registers, so that the first pass's
+// streaming loads find the row in L2 instead of paying the HBM latency.
+template <int M, int C> __device__ __forceinline__ void prefetch_row_l2(const cd *__restrict__ zrow, int c)
+{
+    constexpr int LINES = M / 8; // 128-byte lines of this CTA's share
+    const cd *base = zrow + (size_t) c * M;
+#pragma unroll
+    for (int i = 0; i < (LINES + ROW_THREADS - 1) / ROW_THREADS; ++i) {
+        const int ln = i * ROW_THREADS + (int) threadIdx.x;
+        if (ln < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ln * 8));
+    }
+}
 
 template <int M> __device__ __forceinline__ void stage_row(cd *sm, const cd *__restrict__ zrow, int lt)
 {
@@ -177,14 +196,21 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
 
     const bool odd = (C == 2 && c == 1);
     auto row_ptr = [&](unsigned grp) -> const cd * {
-        const unsigned row = grp * G + g;
+        unsigned row = grp * G + g;
+#ifdef HPXFFT_B200_DIAG_WRAP
+        row &= 63u;
+#endif
         return V + (unsigned long long) (row < nxl ? row : nxl - 1) * pitch;
     };
     if constexpr (C == 1) {
         if (blockIdx.x < ngroups) stage_row<M>(sm, row_ptr(blockIdx.x), lt);
     }
     for (unsigned grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+#ifdef HPXFFT_B200_DIAG_WRAP
+        const unsigned row = (grp * G + g) & 63u;
+#else
         const unsigned row = grp * G + g;
+#endif
         const bool valid = row < nxl;
         const cd *zrow = row_ptr(grp);
         cd v[ROW_PT];
@@ -207,6 +233,10 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
             __syncthreads();
             if (grp + gridDim.x < ngroups) stage_row<M>(sm, row_ptr(grp + gridDim.x), lt);
         }
+#ifndef HPXFFT_B200_NO_ROW_PREFETCH
+        else if (grp + gridDim.x < ngroups)
+            prefetch_row_l2<M, C>(row_ptr(grp + gridDim.x), c);
+#endif
         // rotated == column jB got conj twiddles, its natural output s sits at butterfly output (s+1)&15
         const bool rotated = odd || lt != 0;
         if (odd) {
@@ -248,10 +278,18 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
             cd *pk = nullptr, *pm = nullptr;
             long long step = 0;
             if constexpr (FASTADDR) {
+#ifdef HPXFFT_B200_DIAG_CONTIG_STORE
+                const unsigned k0 = (unsigned) c * (unsigned) M + (unsigned) jA, m0 = MM - k0;
+#else
                 const unsigned k0 = (unsigned) c + (unsigned) C * (unsigned) jA, m0 = MM - k0;
-                pk = dst.base[0] + (unsigned long long) (k0 >> 4) * dst.tile_stride + (unsigned long long) row * CW + (k0 & 15u);
-                pm = dst.base[0] + (unsigned long long) (m0 >> 4) * dst.tile_stride + (unsigned long long) row * CW + (m0 & 15u);
-                step = (long long) ((C * PP) >> 4) * (long long) dst.tile_stride;
+#endif
+                pk = dst.base[0] + (unsigned long long) (k0 >> CW_SHIFT) * dst.tile_stride + (unsigned long long) row * CW + (k0 & (unsigned) (CW - 1));
+                pm = dst.base[0] + (unsigned long long) (m0 >> CW_SHIFT) * dst.tile_stride + (unsigned long long) row * CW + (m0 & (unsigned) (CW - 1));
+#ifdef HPXFFT_B200_DIAG_CONTIG_STORE
+                step = (long long) (PP >> CW_SHIFT) * (long long) dst.tile_stride;
+#else
+                step = (long long) ((C * PP) >> CW_SHIFT) * (long long) dst.tile_stride;
+#endif
             }
 #pragma unroll
             for (int s = 0; s < 16; ++s) {

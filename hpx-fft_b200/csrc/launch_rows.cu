@@ -1,0 +1,75 @@
+// launch_rows.cu -- dispatch of the row (r2c) kernels.
+#include "kernels_rows.cuh"
+#include "launch_util.h"
+
+namespace hpxfft_b200 {
+
+namespace {
+
+template <int M, int C, bool FAST> int launch_rows_big_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+{
+    constexpr size_t smem = row_smem_total<M>();
+    if (int rc = ensure_smem(rows_r2c_kernel<M, C, FAST>, smem, p->device)) return rc;
+    const unsigned ngroups = (nrows + row_group<M>() - 1) / row_group<M>();
+    // one resident CTA per SM (shared memory bound): persistent CTAs amortise the twiddle-table build
+    const int sms = p->sm_count - p->sm_reserve;
+    const unsigned cap = (unsigned) sms / C > 0 ? (unsigned) sms / C : 1u;
+    const unsigned grid = ngroups < cap ? ngroups : cap;
+    if (C > 2 && !p->zraw) return fail(HPXFFT_B200_ESTATE, "long-row scratch missing");
+    rows_r2c_kernel<M, C, FAST><<<dim3(grid, C), ROW_THREADS, smem, p->stream>>>(V, pitch, nrows, dst, p->tw_row, p->zraw);
+    CU(cudaGetLastError());
+    if (C > 2) {
+        const unsigned m = (unsigned) M * C;
+        herm_split_kernel<<<dim3(nrows, (m / 2 + 1 + 255) / 256), 256, 0, p->stream>>>(p->zraw, m, nrows, dst, p->tw_row);
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+template <int M, int C = 1> int launch_rows_big(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+{
+    // fast output addressing: one destination rank and tile-aligned per-s stride (the 1-GPU hot configs)
+    if constexpr (M == 8192 && C <= 2) {
+        if (dst.P == 1) return launch_rows_big_t<M, C, true>(p, dst, nrows, V, pitch);
+    }
+    return launch_rows_big_t<M, C, false>(p, dst, nrows, V, pitch);
+}
+
+template <int M> int launch_rows_tiny(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+{
+    const unsigned block = 128, grid = (nrows + block - 1) / block;
+    rows_r2c_tiny_kernel<M><<<grid, block, 0, p->stream>>>(V, pitch, nrows, dst, p->tw_row);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int rows_launch_count(size_t m) { return m > 16384 ? 2 : 1; }
+
+int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m)
+{
+    if (p->rows_generic) return launch_rows_generic(p, dst, nrows, V, pitch, m);
+    switch (m) {
+    case 1: return launch_rows_tiny<1>(p, dst, nrows, V, pitch);
+    case 2: return launch_rows_tiny<2>(p, dst, nrows, V, pitch);
+    case 4: return launch_rows_tiny<4>(p, dst, nrows, V, pitch);
+    case 8: return launch_rows_tiny<8>(p, dst, nrows, V, pitch);
+    case 16: return launch_rows_tiny<16>(p, dst, nrows, V, pitch);
+    case 32: return launch_rows_big<32>(p, dst, nrows, V, pitch);
+    case 64: return launch_rows_big<64>(p, dst, nrows, V, pitch);
+    case 128: return launch_rows_big<128>(p, dst, nrows, V, pitch);
+    case 256: return launch_rows_big<256>(p, dst, nrows, V, pitch);
+    case 512: return launch_rows_big<512>(p, dst, nrows, V, pitch);
+    case 1024: return launch_rows_big<1024>(p, dst, nrows, V, pitch);
+    case 2048: return launch_rows_big<2048>(p, dst, nrows, V, pitch);
+    case 4096: return launch_rows_big<4096>(p, dst, nrows, V, pitch);
+    case 8192: return launch_rows_big<8192>(p, dst, nrows, V, pitch);
+    case 16384: return launch_rows_big<8192, 2>(p, dst, nrows, V, pitch);
+    case 32768: return launch_rows_big<8192, 4>(p, dst, nrows, V, pitch);
+    case 65536: return launch_rows_big<8192, 8>(p, dst, nrows, V, pitch);
+    default: return fail(HPXFFT_B200_EINVAL, "unsupported row length ny=%zu (ny/2 must be a power of two <= 65536)", 2 * m);
+    }
+}
+
+}  // namespace hpxfft_b200

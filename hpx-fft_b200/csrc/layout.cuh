@@ -16,7 +16,12 @@
 
 namespace hpxfft_b200 {
 
-constexpr int CW = 16;   // columns per tile: 16 complex = 256-byte segments
+#ifndef HPXFFT_B200_CW
+#define HPXFFT_B200_CW 16
+#endif
+constexpr int CW = HPXFFT_B200_CW;   // columns per tile: 16 complex = 256-byte segments
+constexpr int CW_SHIFT = CW == 16 ? 4 : (CW == 32 ? 5 : (CW == 64 ? 6 : -1));
+static_assert(CW_SHIFT > 0, "CW must be 16, 32 or 64");
 constexpr int MAXP = 16; // max ranks
 
 // Destination of the row pass: column k of local row j.
@@ -92,5 +97,12 @@ __device__ __forceinline__ cd *coldst_ptr(const ColDst &d, unsigned kx, unsigned
     }
     return d.base[r] + ((long long) j * (long long) d.pitch[r] + (long long) d.col0[r] + (long long) kl);
 }
+
+// chunked unpack of exchange #2 (pipelined NCCL transport): one dense [nxl][wc_q] block per source rank
+struct UnpackChunk {
+    unsigned long long src_off[MAXP]; // element offset of the block inside the receive buffer
+    unsigned dst_col[MAXP];           // first destination column in V
+    unsigned wc[MAXP];                // block width (0 = nothing from this rank)
+};
 
 }  // namespace hpxfft_b200

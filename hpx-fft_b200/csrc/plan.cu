@@ -1,60 +1,34 @@
-// hpxfft_b200.cu -- plan object and C ABI (include/hpxfft_b200.h) of libhpxfft_b200.so.
+// plan.cu -- plan object and C ABI (include/hpxfft_b200.h) of libhpxfft_b200.so.
 //
 // Host-side counterpart of hpxfft::shared::loop::initialize / fft_2d_r2c_par
 // (core/src/shared/loop.cpp:56-113,158-189) and hpxfft::distributed::loop::initialize / fft_2d_r2c
 // (core/src/distributed/loop.cpp:130-347) of the reference: dimension inference, buffers, "plans"
 // (twiddle tables + kernel selection), communicator, the phase sequence and its timers.
-#include "../../include/hpxfft_b200.h"
+#include "internal.h"
 
-#include "kernels_cols.cuh"
-#include "kernels_misc.cuh"
-#include "kernels_rows.cuh"
-#include "kernels_rows16.cuh"
-
-#include <nccl.h>  // types only: the library is dlopen'ed lazily (see NcclApi) so that a host process
-                   // that already carries its own libnccl.so.2 (e.g. PyTorch's bundled one) is reused
 #include <dlfcn.h>
+#include <sched.h>
 
 #include <cmath>
-#include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
-#include <map>
-#include <string>
-#include <vector>
+#include <fstream>
 
 using namespace hpxfft_b200;
 
 namespace {
 
-thread_local char g_err[512] = "";
-
-int fail(int code, const char *fmt, ...)
-{
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-    return code;
-}
-
-#define CU(call)                                                                                            \
-    do {                                                                                                    \
-        cudaError_t e_ = (call);                                                                            \
-        if (e_ != cudaSuccess)                                                                              \
-            return fail(HPXFFT_B200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
-                        __LINE__);                                                                          \
-    } while (0)
-
-#define NC(call)                                                                                            \
-    do {                                                                                                    \
-        ncclResult_t r_ = (call);                                                                           \
-        if (r_ != ncclSuccess)                                                                              \
+#define NC(call)                                                                                                \
+    do {                                                                                                        \
+        ncclResult_t r_ = (call);                                                                               \
+        if (r_ != ncclSuccess)                                                                                  \
             return fail(HPXFFT_B200_ENCCL, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, \
-                        __LINE__);                                                                          \
+                        __LINE__);                                                                              \
     } while (0)
 
-// NCCL entry points, resolved at first use.
+// NCCL entry points, resolved at first use (a host process that already carries its own libnccl.so.2,
+// e.g. PyTorch's bundled one, is reused).
 struct NcclApi {
     void *handle = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
@@ -94,35 +68,26 @@ int nccl_load()
     return 0;
 }
 
-enum Mode { MODE_SHARED = 0, MODE_SCATTER = 1, MODE_ALL_TO_ALL = 2, MODE_P2P = 3 };
-
-bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
-
-// exp(-2 pi i k / n) rounded from long double; exact on the axes and diagonals so that small
-// integer inputs (the reference's 4x4 known-answer test) transform exactly.
-void make_twiddles(std::vector<double2> &t, size_t n)
-{
-    t.resize(n);
-    const long double PI_L = 3.14159265358979323846264338327950288L;
-    for (size_t k = 0; k < n; ++k) {
-        // reduce to the first octant, evaluate there, map back by symmetry
-        const size_t k8 = (8 * k) / n;           // octant 0..7
-        const bool on_oct = (8 * k) % n == 0;
-        long double c, s; // cos, sin of 2 pi k / n
-        if (on_oct) {
-            static const long double r2 = 0.70710678118654752440084436210484903928L;
-            const long double C[8] = {1, r2, 0, -r2, -1, -r2, 0, r2};
-            const long double S[8] = {0, r2, 1, r2, 0, -r2, -1, -r2};
-            c = C[k8];
-            s = S[k8];
-        } else {
-            const long double a = 2.0L * PI_L * (long double) k / (long double) n;
-            c = cosl(a);
-            s = sinl(a);
-        }
-        t[k] = make_double2((double) c, (double) (-s));
+// closes an open NCCL group on every exit path
+struct NcclGroup {
+    bool open = false;
+    int start()
+    {
+        NC(g_nccl.GroupStart());
+        open = true;
+        return 0;
     }
-}
+    int end()
+    {
+        open = false;
+        NC(g_nccl.GroupEnd());
+        return 0;
+    }
+    ~NcclGroup()
+    {
+        if (open) g_nccl.GroupEnd();
+    }
+};
 
 // [x2][k1] = w_nx^(k1*x2), nx = n1*n2, from the length-nx table
 void make_interlevel(std::vector<double2> &w2, const std::vector<double2> &t, unsigned n1, unsigned n2)
@@ -131,323 +96,6 @@ void make_interlevel(std::vector<double2> &w2, const std::vector<double2> &t, un
     w2.resize(nx);
     for (size_t x2 = 0; x2 < n2; ++x2)
         for (size_t k1 = 0; k1 < n1; ++k1) w2[x2 * n1 + k1] = t[(k1 * x2) % nx];
-}
-
-}  // namespace
-
-struct hpxfft_b200_plan {
-    int rank = 0, P = 1, device = 0, mode = MODE_SHARED;
-    size_t nxl = 0, n_col = 0, ny = 0, cy = 0, nx = 0, m = 0;
-    // column ownership
-    unsigned wq0 = 0, w = 0, c0 = 0, ntiles = 0;
-    std::vector<unsigned> ntiles_of, w_of, c0_of;
-    // column FFT decomposition
-    unsigned n1 = 1, n2 = 1;
-    bool two_level = false;
-    bool rows_generic = false, cols_generic = false; // direct-DFT kernels for lengths that are not powers of two
-    // device buffers
-    double *V = nullptr;   // slab, nxl x n_col doubles
-    cd *bufA = nullptr;    // send buffer of exchange #1 and #2 (nranks > 1, NCCL modes)
-    cd *bufB = nullptr;    // I (intermediate / receive window of exchange #1); receive buffer of #2
-    cd *zraw = nullptr;    // un-split row spectra, only for rows longer than 32768 reals
-    cd *S = nullptr;       // four-step scratch (full array, or an L2-resident ring of strips when fused)
-    bool fused = false;    // level A + level B in one persistent launch
-    bool fused_tma = false; // ... with the warp-specialised TMA-bulk / mbarrier pipeline
-    unsigned lag = 0, nslot = 0, fused_grid = 0;
-    unsigned *ctl = nullptr; // tile counter + per-strip completion counters
-    cd *tw_row = nullptr, *tw_col = nullptr;
-    cd *tw_il = nullptr;   // inter-level twiddles of the four-step column FFT, [x2][k1] = w_nx^(k1*x2)
-    size_t bytesA = 0, bytesB = 0, bytesS = 0;
-    // Experimental (single rank only): extra rows of padding between the column tiles of I, so that the tile
-    // stride is not a power of two (suspected DRAM channel aliasing of the 256-byte segment traffic).
-    size_t tile_pad_rows = 0;
-    // p2p
-    std::vector<void *> peerI, peerV;
-    bool ipc_imported = false;
-    // pipelined exchange (NCCL modes): sub-slab chunks of rows / strips, communication on its own stream
-    int chunks_r = 1, chunks_c = 1;
-    cd *bufC = nullptr;             // receive buffer of exchange #2 when it overlaps the column pass
-    cudaStream_t cstream = nullptr; // high-priority communication stream
-    std::vector<cudaEvent_t> ev_chunk; // [chunks_r + chunks_c + 2]
-    int sm_reserve = 0;             // SMs left free for NCCL's kernels while the row kernel runs
-    // execution
-    cudaStream_t stream = nullptr;
-    // One event set per execute since the last reset (ring of EV_SETS): lets a benchmark launch K
-    // transforms back to back and still read per-phase / per-kernel averages afterwards.
-    static constexpr int EV_SETS = 64, EV_PER_SET = 7;
-    std::vector<cudaEvent_t> evs;   // EV_SETS * EV_PER_SET
-    cudaEvent_t ev_io[2] = {};      // upload / download timing
-    long nrec = 0;                  // executes enqueued since the last reset
-    ncclComm_t comm = nullptr;
-    int *d_barrier = nullptr;
-    int launches = 0;
-    std::map<std::string, double> meas;
-    std::string plan_flag, row_desc, col_desc, col_desc_extra;
-};
-
-namespace {
-
-// ------------------------------------------------------------------------------------------------
-// kernel dispatch
-// ------------------------------------------------------------------------------------------------
-template <class K> int set_smem(K kernel, size_t bytes)
-{
-    if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
-    return 0;
-}
-
-template <int M, int C, bool FAST> int launch_rows_big_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
-{
-    constexpr size_t smem = row_smem_total<M>();
-    static int configured = -1;
-    if (configured != p->device) {
-        if (int rc = set_smem(rows_r2c_kernel<M, C, FAST>, smem)) return rc;
-        configured = p->device;
-    }
-    const unsigned ngroups = (nrows + row_group<M>() - 1) / row_group<M>();
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
-    // one resident CTA per SM (shared memory bound): persistent CTAs amortise the twiddle-table build
-    sms -= p->sm_reserve;
-    const unsigned cap = (unsigned) sms / C > 0 ? (unsigned) sms / C : 1u;
-    const unsigned grid = ngroups < cap ? ngroups : cap;
-    if (C > 2 && !p->zraw) return fail(HPXFFT_B200_ESTATE, "long-row scratch missing");
-    rows_r2c_kernel<M, C, FAST><<<dim3(grid, C), ROW_THREADS, smem, p->stream>>>(V, pitch, nrows, dst, p->tw_row, p->zraw);
-    CU(cudaGetLastError());
-    if (C > 2) {
-        const unsigned m = (unsigned) M * C;
-        herm_split_kernel<<<dim3(nrows, (m / 2 + 1 + 255) / 256), 256, 0, p->stream>>>(p->zraw, m, nrows, dst, p->tw_row);
-        CU(cudaGetLastError());
-    }
-    return 0;
-}
-
-template <int M, int C = 1> int launch_rows_big(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
-{
-    // fast output addressing: one destination rank and tile-aligned per-s stride (the 1-GPU hot configs)
-    if constexpr (M == 8192 && C <= 2) {
-        if (dst.P == 1) return launch_rows_big_t<M, C, true>(p, dst, nrows, V, pitch);
-    }
-    return launch_rows_big_t<M, C, false>(p, dst, nrows, V, pitch);
-}
-
-// EXPERIMENTAL 512-thread row kernel (kernels_rows16.cuh), opt-in with HPXFFT_B200_ROWS16=1
-bool rows16_enabled()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("HPXFFT_B200_ROWS16");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
-
-template <bool FAST> int launch_rows16_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
-{
-    static int configured = -1;
-    if (configured != p->device) {
-        if (int rc = set_smem(rows16_r2c_kernel<FAST>, rows16::SMEM)) return rc;
-        configured = p->device;
-    }
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
-    sms -= p->sm_reserve;
-    const unsigned grid = nrows < (unsigned) sms ? nrows : (unsigned) sms;
-    rows16_r2c_kernel<FAST><<<grid, rows16::T, rows16::SMEM, p->stream>>>(V, pitch, nrows, dst, p->tw_row);
-    CU(cudaGetLastError());
-    return 0;
-}
-
-template <int M> int launch_rows_tiny(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
-{
-    const unsigned block = 128, grid = (nrows + block - 1) / block;
-    rows_r2c_tiny_kernel<M><<<grid, block, 0, p->stream>>>(V, pitch, nrows, dst, p->tw_row);
-    CU(cudaGetLastError());
-    return 0;
-}
-
-int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m)
-{
-    if (p->rows_generic) {
-        const unsigned ny = (unsigned) (2 * m), cy = ny / 2 + 1;
-        rows_generic_kernel<<<dim3(nrows, (cy + 127) / 128), 128, 0, p->stream>>>((const double *) V, 2 * pitch, nrows, ny, dst, p->tw_row);
-        CU(cudaGetLastError());
-        return 0;
-    }
-    switch (m) {
-    case 1: return launch_rows_tiny<1>(p, dst, nrows, V, pitch);
-    case 2: return launch_rows_tiny<2>(p, dst, nrows, V, pitch);
-    case 4: return launch_rows_tiny<4>(p, dst, nrows, V, pitch);
-    case 8: return launch_rows_tiny<8>(p, dst, nrows, V, pitch);
-    case 16: return launch_rows_tiny<16>(p, dst, nrows, V, pitch);
-    case 32: return launch_rows_big<32>(p, dst, nrows, V, pitch);
-    case 64: return launch_rows_big<64>(p, dst, nrows, V, pitch);
-    case 128: return launch_rows_big<128>(p, dst, nrows, V, pitch);
-    case 256: return launch_rows_big<256>(p, dst, nrows, V, pitch);
-    case 512: return launch_rows_big<512>(p, dst, nrows, V, pitch);
-    case 1024: return launch_rows_big<1024>(p, dst, nrows, V, pitch);
-    case 2048: return launch_rows_big<2048>(p, dst, nrows, V, pitch);
-    case 4096: return launch_rows_big<4096>(p, dst, nrows, V, pitch);
-    case 8192:
-        if (rows16_enabled()) return dst.P == 1 ? launch_rows16_t<true>(p, dst, nrows, V, pitch) : launch_rows16_t<false>(p, dst, nrows, V, pitch);
-        return launch_rows_big<8192>(p, dst, nrows, V, pitch);
-    case 16384: return launch_rows_big<8192, 2>(p, dst, nrows, V, pitch);
-    case 32768: return launch_rows_big<8192, 4>(p, dst, nrows, V, pitch);
-    case 65536: return launch_rows_big<8192, 8>(p, dst, nrows, V, pitch);
-    default: return fail(HPXFFT_B200_EINVAL, "unsupported row length ny=%zu (ny/2 must be a power of two <= 65536)", 2 * m);
-    }
-}
-
-template <int N> int launch_cols_single(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles)
-{
-    constexpr size_t smem = single_smem_bytes<N>();
-    static int configured = -1;
-    if (configured != p->device) {
-        if (int rc = set_smem(cols_single_kernel<N>, smem)) return rc;
-        configured = p->device;
-    }
-    cols_single_kernel<N><<<ntiles, col_threads(N), smem, p->stream>>>(in, out, p->tw_col);
-    CU(cudaGetLastError());
-    return 0;
-}
-
-template <int N1> int launch_cols_A(const hpxfft_b200_plan *p, const InterView &in, cd *S, unsigned n2, unsigned ntiles)
-{
-    constexpr size_t smem = levelA_smem_bytes<N1>();
-    static int configured = -1;
-    if (configured != p->device) {
-        if (int rc = set_smem(cols_levelA_kernel<N1>, smem)) return rc;
-        configured = p->device;
-    }
-    cols_levelA_kernel<N1><<<dim3(n2, ntiles), col_threads(N1), smem, p->stream>>>(in, S, n2, p->tw_col, p->tw_il);
-    CU(cudaGetLastError());
-    return 0;
-}
-
-template <int N2> int launch_cols_B(const hpxfft_b200_plan *p, const cd *S, const ColDst &out, unsigned n1, unsigned ntiles)
-{
-    constexpr size_t smem = single_smem_bytes<N2>();
-    static int configured = -1;
-    if (configured != p->device) {
-        if (int rc = set_smem(cols_levelB_kernel<N2>, smem)) return rc;
-        configured = p->device;
-    }
-    cols_levelB_kernel<N2><<<dim3(n1, ntiles), col_threads(N2), smem, p->stream>>>(S, out, n1, p->tw_col);
-    CU(cudaGetLastError());
-    return 0;
-}
-
-#define DISPATCH_POW2(FN, N, LO, ...)                                                         \
-    switch (N) {                                                                              \
-    case 1: if (LO <= 1) return FN<1>(__VA_ARGS__); break;                                    \
-    case 2: if (LO <= 2) return FN<2>(__VA_ARGS__); break;                                    \
-    case 4: if (LO <= 4) return FN<4>(__VA_ARGS__); break;                                    \
-    case 8: if (LO <= 8) return FN<8>(__VA_ARGS__); break;                                    \
-    case 16: return FN<16>(__VA_ARGS__);                                                      \
-    case 32: return FN<32>(__VA_ARGS__);                                                      \
-    case 64: return FN<64>(__VA_ARGS__);                                                      \
-    case 128: return FN<128>(__VA_ARGS__);                                                    \
-    case 256: return FN<256>(__VA_ARGS__);                                                    \
-    case 512: return FN<512>(__VA_ARGS__);                                                    \
-    default: break;                                                                           \
-    }
-
-int launch_cols(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles, cd *S, unsigned nx,
-                unsigned n1, unsigned n2, bool two_level, int *launches, cudaEvent_t mid = nullptr)
-{
-    if (p->cols_generic) {
-        if (launches) *launches += 1;
-        if (mid) CU(cudaEventRecord(mid, p->stream));
-        cols_generic_kernel<<<dim3(ntiles * CW, (nx + 127) / 128), 128, 0, p->stream>>>(in, out, nx, p->tw_col);
-        CU(cudaGetLastError());
-        return 0;
-    }
-    if (!two_level) {
-        if (launches) *launches += 1;
-        if (mid) CU(cudaEventRecord(mid, p->stream));
-        if (nx <= 256) { DISPATCH_POW2(launch_cols_single, nx, 1, p, in, out, ntiles) }
-        return fail(HPXFFT_B200_EINVAL, "unsupported single-level column length %u", nx);
-    }
-    if (launches) *launches += 2;
-    {
-        auto a = [&]() -> int {
-            DISPATCH_POW2(launch_cols_A, n1, 16, p, in, S, n2, ntiles)
-            return fail(HPXFFT_B200_EINVAL, "unsupported level-A length %u", n1);
-        };
-        if (int rc = a()) return rc;
-        if (mid) CU(cudaEventRecord(mid, p->stream));
-    }
-    DISPATCH_POW2(launch_cols_B, n2, 16, p, S, out, n1, ntiles)
-    return fail(HPXFFT_B200_EINVAL, "unsupported level-B length %u", n2);
-}
-
-template <int N1, int N2> int fused_occupancy(int *blocks_per_sm, bool tma)
-{
-    if (tma) {
-        constexpr size_t smem = tma_smem_bytes<N1, N2>();
-        if (int rc = set_smem(cols_fused_tma_kernel<N1, N2>, smem)) return rc;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cols_fused_tma_kernel<N1, N2>, tma_threads<N1, N2>(), smem));
-        return 0;
-    }
-    constexpr size_t smem = fused_smem_bytes<N1, N2>();
-    if (int rc = set_smem(cols_fused_kernel<N1, N2>, smem)) return rc;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cols_fused_kernel<N1, N2>, fused_threads<N1, N2>(), smem));
-    return 0;
-}
-
-template <int N1, int N2>
-int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ct0, unsigned ntiles)
-{
-    constexpr size_t smem = fused_smem_bytes<N1, N2>();
-    static int configured = -1;
-    if (configured != p->device) {
-        if (int rc = set_smem(cols_fused_kernel<N1, N2>, smem)) return rc;
-        if (int rc = set_smem(cols_fused_tma_kernel<N1, N2>, tma_smem_bytes<N1, N2>())) return rc;
-        configured = p->device;
-    }
-    CU(cudaMemsetAsync(p->ctl, 0, (1 + 2 * (size_t) ntiles) * sizeof(unsigned), p->stream));
-    FusedCtl ctl;
-    ctl.counter = p->ctl;
-    ctl.doneA = p->ctl + 1;
-    ctl.doneB = p->ctl + 1 + ntiles;
-    ctl.lag = p->lag;
-    ctl.nslot = p->nslot;
-    ctl.ct0 = ct0;
-    if (ctl.nslot > ntiles) ctl.nslot = ntiles; // a short chunk needs (and may use) no more slots than strips
-    {
-        static int discard = -1;
-        if (discard < 0) {
-            const char *e = getenv("HPXFFT_B200_DISCARD");
-            discard = (e && e[0] == '0') ? 0 : 1;
-        }
-        ctl.discard = (unsigned) discard;
-    }
-    if (p->fused_tma)
-        cols_fused_tma_kernel<N1, N2><<<p->fused_grid, tma_threads<N1, N2>(), tma_smem_bytes<N1, N2>(), p->stream>>>(in, p->S, out, p->tw_col,
-                                                                                                          p->tw_il, ntiles, ctl);
-    else
-        cols_fused_kernel<N1, N2><<<p->fused_grid, fused_threads<N1, N2>(), smem, p->stream>>>(in, p->S, out, p->tw_col, p->tw_il, ntiles, ctl);
-    CU(cudaGetLastError());
-    return 0;
-}
-
-#define FUSED_PAIRS(X) X(32, 16) X(32, 32) X(64, 32) X(64, 64) X(128, 64) X(128, 128) X(256, 128) X(256, 256) X(512, 256) X(512, 512)
-
-int launch_cols_fused(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ct0, unsigned ntiles)
-{
-    if (ntiles == 0) return 0;
-#define X(A, B) if (p->n1 == A && p->n2 == B) return launch_cols_fused_t<A, B>(p, in, out, ct0, ntiles);
-    FUSED_PAIRS(X)
-#undef X
-    return fail(HPXFFT_B200_EINVAL, "no fused column kernel for %u x %u", p->n1, p->n2);
-}
-
-int fused_blocks_per_sm(unsigned n1, unsigned n2, int *bps, bool tma)
-{
-#define X(A, B) if (n1 == A && n2 == B) return fused_occupancy<A, B>(bps, tma);
-    FUSED_PAIRS(X)
-#undef X
-    return fail(HPXFFT_B200_EINVAL, "no fused column kernel for %u x %u", n1, n2);
 }
 
 void choose_col_split(size_t nx, unsigned &n1, unsigned &n2, bool &two_level)
@@ -482,24 +130,36 @@ int parse_comm_flag(const char *f, int *mode)
     return -1;
 }
 
-int fill_rowdst(const hpxfft_b200_plan *p, RowDst &d)
+int env_int(const char *name, int dflt)
 {
-    d.tile_stride = (unsigned long long) (p->nxl + p->tile_pad_rows) * CW;
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+// elements of rank q's I-layout block as written by ONE source rank
+unsigned long long iblock(const hpxfft_b200_plan *p, int q) { return (unsigned long long) p->ntiles_of[q] * p->nxl * CW; }
+
+// Destination of the row pass.  Own columns always go straight into this rank's I; remote columns go into
+// the peer's I (TR_FUSED) or into the send staging buffer bufA (TR_NCCL, TR_CE).
+// row0: first local row of the launch (sub-slab chunks).
+void fill_rowdst(const hpxfft_b200_plan *p, RowDst &d, size_t row0 = 0)
+{
+    d.tile_stride = (unsigned long long) p->nxl * CW;
     d.cy = (unsigned) p->cy;
     d.wq0 = p->wq0;
     d.P = (unsigned) p->P;
     unsigned long long off = 0;
     for (int q = 0; q < p->P; ++q) {
-        const unsigned long long blk = (unsigned long long) p->ntiles_of[q] * p->nxl * CW;
+        const unsigned long long blk = iblock(p, q);
         if (q == p->rank)
-            d.base[q] = p->bufB + (unsigned long long) p->rank * ((unsigned long long) p->ntiles * p->nxl * CW);
-        else if (p->mode == MODE_P2P)
+            d.base[q] = p->bufB + (unsigned long long) p->rank * blk;
+        else if (p->transport == TR_FUSED)
             d.base[q] = (cd *) p->peerI[q] + (unsigned long long) p->rank * blk;
         else
             d.base[q] = p->bufA + off;
+        d.base[q] += (unsigned long long) row0 * CW;
         off += blk;
     }
-    return 0;
 }
 
 void fill_coldst(const hpxfft_b200_plan *p, ColDst &d)
@@ -512,7 +172,7 @@ void fill_coldst(const hpxfft_b200_plan *p, ColDst &d)
             d.base[r] = (cd *) p->V;
             d.pitch[r] = (unsigned) p->cy;
             d.col0[r] = (int) p->c0;
-        } else if (p->mode == MODE_P2P) {
+        } else if (p->transport == TR_FUSED) {
             d.base[r] = (cd *) p->peerV[r];
             d.pitch[r] = (unsigned) p->cy;
             d.col0[r] = (int) p->c0;
@@ -524,90 +184,97 @@ void fill_coldst(const hpxfft_b200_plan *p, ColDst &d)
     }
 }
 
+void fill_interview(const hpxfft_b200_plan *p, InterView &iv)
+{
+    iv.base = p->bufB;
+    iv.nxl = (unsigned) p->nxl;
+    iv.shift = pow2_shift(iv.nxl);
+    iv.tile_stride = (unsigned long long) p->nxl * CW;
+    iv.rank_stride = (unsigned long long) p->ntiles * p->nxl * CW;
+}
+
 bool a2a_stepwise()
 {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("HPXFFT_B200_A2A_STEPWISE");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
+    static const int v = env_int("HPXFFT_B200_A2A_STEPWISE", 0);
     return v == 1;
 }
 
+// stream-ordered barrier across the ranks: nobody passes before everybody's earlier work on `stream` is done
 int barrier_on_stream(hpxfft_b200_plan *p)
 {
     NC(g_nccl.AllReduce(p->d_barrier, p->d_barrier, 1, ncclInt, ncclSum, p->comm, p->stream));
     return 0;
 }
 
-// exchange #1: block (r -> q) = I-layout tiles of rank q's columns for my rows
-int exchange1(hpxfft_b200_plan *p)
+// ---- TR_NCCL ---------------------------------------------------------------------------------------------
+// all_to_all: every rank's P-1 sends and receives in ONE NCCL group (rotation order), the counterpart of
+//             hpx::collectives::all_to_all (core/src/distributed/loop.cpp:72-84).
+// scatter   : P rooted scatters, ONE NCCL group per root issued in root order -- the literal shape of
+//             scatter_to / scatter_from on P communicators (core/src/distributed/loop.cpp:39-69,158-167).  NCCL runs the
+//             groups of one communicator one after the other, so only one root sends at a time.
+template <class SendFn, class RecvFn> int exchange_groups(hpxfft_b200_plan *p, cudaStream_t, SendFn send, RecvFn recv)
 {
     const int P = p->P, me = p->rank;
-    std::vector<unsigned long long> soff(P + 1, 0);
-    for (int q = 0; q < P; ++q) soff[q + 1] = soff[q] + (unsigned long long) p->ntiles_of[q] * p->nxl * CW;
-    const unsigned long long rblk = (unsigned long long) p->ntiles * p->nxl * CW; // what every peer sends me
-    if (p->mode == MODE_ALL_TO_ALL) {
-        // rotation schedule: step s pairs every rank with (me+s) / (me-s).  Either all P-1 steps in one NCCL
-        // group (default) or one group per step (HPXFFT_B200_A2A_STEPWISE=1), which keeps each NVLink
-        // transfer at full per-pair channel count when P is large.
-        if (!a2a_stepwise()) NC(g_nccl.GroupStart());
-        for (int s = 1; s < P; ++s) {
-            const int to = (me + s) % P, from = (me - s + P) % P;
-            if (a2a_stepwise()) NC(g_nccl.GroupStart());
-            NC(g_nccl.Send(p->bufA + soff[to], (soff[to + 1] - soff[to]) * 2, ncclDouble, to, p->comm, p->stream));
-            NC(g_nccl.Recv(p->bufB + (unsigned long long) from * rblk, rblk * 2, ncclDouble, from, p->comm, p->stream));
-            if (a2a_stepwise()) NC(g_nccl.GroupEnd());
-        }
-        if (!a2a_stepwise()) NC(g_nccl.GroupEnd());
-    } else { // scatter: one rooted scatter per locality, all in flight together like the reference's
-             // asynchronous scatter_to / scatter_from futures (core/src/distributed/loop.cpp:158-167)
-        NC(g_nccl.GroupStart());
+    NcclGroup g;
+    if (p->mode == MODE_SCATTER) {
         for (int root = 0; root < P; ++root) {
+            if (int rc = g.start()) return rc;
             if (root == me) {
-                for (int to = 0; to < P; ++to)
-                    if (to != me)
-                        NC(g_nccl.Send(p->bufA + soff[to], (soff[to + 1] - soff[to]) * 2, ncclDouble, to, p->comm, p->stream));
-            } else {
-                NC(g_nccl.Recv(p->bufB + (unsigned long long) root * rblk, rblk * 2, ncclDouble, root, p->comm, p->stream));
-            }
+                for (int s = 1; s < P; ++s)
+                    if (int rc = send((me + s) % P)) return rc;
+            } else if (int rc = recv(root))
+                return rc;
+            if (int rc = g.end()) return rc;
         }
-        NC(g_nccl.GroupEnd());
+        return 0;
     }
+    const bool stepwise = a2a_stepwise();
+    if (!stepwise)
+        if (int rc = g.start()) return rc;
+    for (int s = 1; s < P; ++s) {
+        if (stepwise)
+            if (int rc = g.start()) return rc;
+        if (int rc = send((me + s) % P)) return rc;
+        if (int rc = recv((me - s + P) % P)) return rc;
+        if (stepwise)
+            if (int rc = g.end()) return rc;
+    }
+    if (!stepwise)
+        if (int rc = g.end()) return rc;
     return 0;
 }
 
-// exchange #2: block (q -> r) = dense [nxl][w_q] result rows of rank r
-int exchange2(hpxfft_b200_plan *p)
+// exchange #1: block (r -> q) = I-layout tiles of rank q's columns for my rows
+int exchange1_nccl(hpxfft_b200_plan *p)
 {
-    const int P = p->P, me = p->rank;
+    std::vector<unsigned long long> soff(p->P + 1, 0);
+    for (int q = 0; q < p->P; ++q) soff[q + 1] = soff[q] + iblock(p, q);
+    const unsigned long long rblk = iblock(p, p->rank); // what every peer sends me
+    auto send = [&](int to) -> int {
+        NC(g_nccl.Send(p->bufA + soff[to], (soff[to + 1] - soff[to]) * 2, ncclDouble, to, p->comm, p->stream));
+        return 0;
+    };
+    auto recv = [&](int from) -> int {
+        NC(g_nccl.Recv(p->bufB + (unsigned long long) from * rblk, rblk * 2, ncclDouble, from, p->comm, p->stream));
+        return 0;
+    };
+    return exchange_groups(p, p->stream, send, recv);
+}
+
+// exchange #2: block (q -> r) = dense [nxl][w_q] result rows of rank r
+int exchange2_nccl(hpxfft_b200_plan *p)
+{
     const unsigned long long sblk = (unsigned long long) p->nxl * p->w;
-    if (p->mode == MODE_ALL_TO_ALL) {
-        if (!a2a_stepwise()) NC(g_nccl.GroupStart());
-        for (int s = 1; s < P; ++s) {
-            const int to = (me + s) % P, from = (me - s + P) % P;
-            if (a2a_stepwise()) NC(g_nccl.GroupStart());
-            NC(g_nccl.Send(p->bufA + (unsigned long long) to * sblk, sblk * 2, ncclDouble, to, p->comm, p->stream));
-            NC(g_nccl.Recv(p->bufB + (unsigned long long) p->nxl * p->c0_of[from], (unsigned long long) p->nxl * p->w_of[from] * 2,
-                        ncclDouble, from, p->comm, p->stream));
-            if (a2a_stepwise()) NC(g_nccl.GroupEnd());
-        }
-        if (!a2a_stepwise()) NC(g_nccl.GroupEnd());
-    } else {
-        NC(g_nccl.GroupStart());
-        for (int root = 0; root < P; ++root) {
-            if (root == me) {
-                for (int to = 0; to < P; ++to)
-                    if (to != me)
-                        NC(g_nccl.Send(p->bufA + (unsigned long long) to * sblk, sblk * 2, ncclDouble, to, p->comm, p->stream));
-            } else {
-                NC(g_nccl.Recv(p->bufB + (unsigned long long) p->nxl * p->c0_of[root],
-                            (unsigned long long) p->nxl * p->w_of[root] * 2, ncclDouble, root, p->comm, p->stream));
-            }
-        }
-        NC(g_nccl.GroupEnd());
-    }
-    return 0;
+    auto send = [&](int to) -> int {
+        NC(g_nccl.Send(p->bufA + (unsigned long long) to * sblk, sblk * 2, ncclDouble, to, p->comm, p->stream));
+        return 0;
+    };
+    auto recv = [&](int from) -> int {
+        NC(g_nccl.Recv(p->bufB + (unsigned long long) p->nxl * p->c0_of[from], (unsigned long long) p->nxl * p->w_of[from] * 2, ncclDouble,
+                       from, p->comm, p->stream));
+        return 0;
+    };
+    return exchange_groups(p, p->stream, send, recv);
 }
 
 // strip range [t0, t1) and column range of chunk t when `ntiles` strips / `w` columns are cut into `nch` chunks
@@ -621,45 +288,30 @@ void chunk_bounds(unsigned ntiles, unsigned w, int nch, int t, unsigned &t0, uns
     wc = cend > col0 ? cend - col0 : 0;
 }
 
-// group of sends/recvs of one exchange chunk; `order` = rotation (all_to_all) or root-major (scatter)
-template <class SendFn, class RecvFn> int exchange_group(hpxfft_b200_plan *p, SendFn send, RecvFn recv)
+cudaEvent_t *event_set(hpxfft_b200_plan *p)
 {
-    const int P = p->P, me = p->rank;
-    NC(g_nccl.GroupStart());
-    if (p->mode == MODE_ALL_TO_ALL) {
-        for (int s = 1; s < P; ++s) {
-            if (int rc = send((me + s) % P)) return rc;
-            if (int rc = recv((me - s + P) % P)) return rc;
-        }
-    } else {
-        for (int root = 0; root < P; ++root) {
-            if (root == me) {
-                for (int to = 0; to < P; ++to)
-                    if (to != me)
-                        if (int rc = send(to)) return rc;
-            } else if (int rc = recv(root))
-                return rc;
-        }
-    }
-    NC(g_nccl.GroupEnd());
-    return 0;
+    cudaEvent_t *ev = p->evs.data() + (size_t) (p->nrec % hpxfft_b200_plan::EV_SETS) * hpxfft_b200_plan::EV_PER_SET;
+    return ev;
 }
 
-// NCCL modes with sub-slab pipelining: the exchange of row chunk s overlaps the row FFTs of chunk s+1,
-// the exchange (+ unpack) of strip chunk t overlaps the column FFTs of chunk t+1.
-int enqueue_transform_pipelined(hpxfft_b200_plan *p)
+// ---- TR_NCCL with sub-slab pipelining (opt-in, HPXFFT_B200_CHUNKS with HPXFFT_B200_A2A=nccl) --------------------
+// the exchange of row chunk s overlaps the row FFTs of chunk s+1, the exchange (+ unpack) of strip chunk t
+// overlaps the column FFTs of chunk t+1.  I is chunk-major here: [r][s][ct][js][c].
+int enqueue_transform_nccl_pipelined(hpxfft_b200_plan *p)
 {
     const int P = p->P, me = p->rank, Sr = p->chunks_r, Sc = p->chunks_c;
     int launches = 0;
     const size_t nxs = p->nxl / Sr;
-    cudaEvent_t *ev = p->evs.data() + (size_t) (p->nrec % hpxfft_b200_plan::EV_SETS) * hpxfft_b200_plan::EV_PER_SET;
+    cudaEvent_t *ev = event_set(p);
+    const long set = p->nrec % hpxfft_b200_plan::EV_SETS;
     p->nrec += 1;
     cudaEvent_t *evr = p->ev_chunk.data(), *evc = p->ev_chunk.data() + Sr;
-    cudaEvent_t ev_x1 = p->ev_chunk[Sr + Sc], ev_x2 = p->ev_chunk[Sr + Sc + 1];
+    cudaEvent_t ev_x1 = p->ev_peer[0], ev_x2 = p->ev_peer[1];
+    cudaEvent_t *evm = p->ev_comm.data() + (size_t) set * 4;
 
     std::vector<unsigned long long> soff(P + 1, 0);
-    for (int q = 0; q < P; ++q) soff[q + 1] = soff[q] + (unsigned long long) p->ntiles_of[q] * p->nxl * CW;
-    const unsigned long long rblk = (unsigned long long) p->ntiles * p->nxl * CW;
+    for (int q = 0; q < P; ++q) soff[q + 1] = soff[q] + iblock(p, q);
+    const unsigned long long rblk = iblock(p, me);
 
     CU(cudaEventRecord(ev[0], p->stream));
     // the communication stream must not start before everything previously enqueued on the main stream
@@ -676,9 +328,10 @@ int enqueue_transform_pipelined(hpxfft_b200_plan *p)
             rd.base[q] = (q == me ? p->bufB + (unsigned long long) me * rblk : p->bufA + soff[q]) + (unsigned long long) s * cs;
         }
         if (int rc = launch_rows(p, rd, (unsigned) nxs, (const cd *) p->V + (size_t) s * nxs * p->cy, (unsigned) p->cy, p->m)) return rc;
-        launches += 1 + (p->m > 16384 ? 1 : 0);
+        launches += rows_launch_count(p->m);
         CU(cudaEventRecord(evr[s], p->stream));
         CU(cudaStreamWaitEvent(p->cstream, evr[s], 0));
+        if (s == 0) CU(cudaEventRecord(evm[0], p->cstream));
         auto send = [&](int to) -> int {
             const unsigned long long cs = (unsigned long long) p->ntiles_of[to] * nxs * CW;
             NC(g_nccl.Send(p->bufA + soff[to] + (unsigned long long) s * cs, cs * 2, ncclDouble, to, p->comm, p->cstream));
@@ -690,9 +343,10 @@ int enqueue_transform_pipelined(hpxfft_b200_plan *p)
                            p->cstream));
             return 0;
         };
-        if (int rc = exchange_group(p, send, recv)) return rc;
+        if (int rc = exchange_groups(p, p->cstream, send, recv)) return rc;
     }
     CU(cudaEventRecord(ev[1], p->stream));
+    CU(cudaEventRecord(evm[1], p->cstream));
     CU(cudaEventRecord(ev_x1, p->cstream));
     CU(cudaStreamWaitEvent(p->stream, ev_x1, 0));
     CU(cudaEventRecord(ev[2], p->stream));
@@ -734,6 +388,7 @@ int enqueue_transform_pipelined(hpxfft_b200_plan *p)
         }
         CU(cudaEventRecord(evc[t], p->stream));
         CU(cudaStreamWaitEvent(p->cstream, evc[t], 0));
+        if (t == 0) CU(cudaEventRecord(evm[2], p->cstream));
         UnpackChunk u;
         bool any = false;
         for (int q = 0; q < P; ++q) {
@@ -756,14 +411,14 @@ int enqueue_transform_pipelined(hpxfft_b200_plan *p)
             NC(g_nccl.Recv(p->bufC + u.src_off[from], (unsigned long long) p->nxl * u.wc[from] * 2, ncclDouble, from, p->comm, p->cstream));
             return 0;
         };
-        if (int rc = exchange_group(p, send, recv)) return rc;
+        if (int rc = exchange_groups(p, p->cstream, send, recv)) return rc;
         if (any) {
-            unpack_chunk_kernel<<<dim3((unsigned) p->nxl, (unsigned) P), 256, 0, p->cstream>>>(p->bufC, (cd *) p->V, (unsigned) p->cy, u);
-            CU(cudaGetLastError());
+            if (int rc = launch_unpack_chunk(p, u, p->cstream)) return rc;
             launches += 1;
         }
     }
     CU(cudaEventRecord(ev[3], p->stream));
+    CU(cudaEventRecord(evm[3], p->cstream));
     CU(cudaEventRecord(ev_x2, p->cstream));
     CU(cudaStreamWaitEvent(p->stream, ev_x2, 0));
     CU(cudaEventRecord(ev[4], p->stream));
@@ -772,36 +427,129 @@ int enqueue_transform_pipelined(hpxfft_b200_plan *p)
     return 0;
 }
 
+// ---- TR_CE: copy-engine all-to-all over the peers' IPC windows ---------------------------------------------------
+// The FFT kernels write remote blocks into the local staging buffer bufA; cudaMemcpy2DAsync peer copies (one
+// stream per peer, no SMs) push them into the owners' windows: exchange #1 into the peer's I, exchange #2
+// straight into the peer's slab V (strided 2-D copy -- no unpack pass).  Rows and strips are cut into
+// chunks so that the copies of chunk s run while chunk s+1 is being computed.  A 1-int NCCL all-reduce on
+// the main stream is the stream-ordered barrier that tells every rank its window is complete.
+int enqueue_transform_ce(hpxfft_b200_plan *p)
+{
+    const int P = p->P, me = p->rank, Sr = p->chunks_r, Sc = p->chunks_c;
+    int launches = 0;
+    const size_t nxs = p->nxl / Sr;
+    cudaEvent_t *ev = event_set(p);
+    const long set = p->nrec % hpxfft_b200_plan::EV_SETS;
+    p->nrec += 1;
+    cudaEvent_t *evr = p->ev_chunk.data(), *evc = p->ev_chunk.data() + Sr;
+    cudaEvent_t *evm = p->ev_comm.data() + (size_t) set * 4;
+    const int first_peer = (me + 1) % P;
+
+    std::vector<unsigned long long> soff(P + 1, 0);
+    for (int q = 0; q < P; ++q) soff[q + 1] = soff[q] + iblock(p, q);
+
+    CU(cudaEventRecord(ev[0], p->stream));
+    // ---- dimension 1
+    for (int s = 0; s < Sr; ++s) {
+        RowDst rd;
+        fill_rowdst(p, rd, (size_t) s * nxs);
+        if (int rc = launch_rows(p, rd, (unsigned) nxs, (const cd *) p->V + (size_t) s * nxs * p->cy, (unsigned) p->cy, p->m)) return rc;
+        launches += rows_launch_count(p->m);
+        CU(cudaEventRecord(evr[s], p->stream));
+        for (int k = 1; k < P; ++k) {
+            const int q = (me + k) % P;
+            cudaStream_t cs = p->pstream[q];
+            CU(cudaStreamWaitEvent(cs, evr[s], 0));
+            if (s == 0 && q == first_peer) CU(cudaEventRecord(evm[0], cs));
+            const cd *src = p->bufA + soff[q] + (unsigned long long) s * nxs * CW;
+            cd *dst = (cd *) p->peerI[q] + (unsigned long long) me * iblock(p, q) + (unsigned long long) s * nxs * CW;
+            if (Sr == 1)
+                CU(cudaMemcpyAsync(dst, src, iblock(p, q) * sizeof(cd), cudaMemcpyDeviceToDevice, cs));
+            else
+                CU(cudaMemcpy2DAsync(dst, p->nxl * CW * sizeof(cd), src, p->nxl * CW * sizeof(cd), nxs * CW * sizeof(cd), p->ntiles_of[q],
+                                     cudaMemcpyDeviceToDevice, cs));
+        }
+    }
+    CU(cudaEventRecord(ev[1], p->stream));
+    for (int k = 1; k < P; ++k) {
+        const int q = (me + k) % P;
+        CU(cudaEventRecord(p->ev_peer[q], p->pstream[q]));
+        CU(cudaStreamWaitEvent(p->stream, p->ev_peer[q], 0));
+    }
+    CU(cudaEventRecord(evm[1], p->stream));
+    if (int rc = barrier_on_stream(p)) return rc;
+    CU(cudaEventRecord(ev[2], p->stream));
+    CU(cudaEventRecord(ev[6], p->stream));
+
+    // ---- dimension 2
+    InterView iv;
+    fill_interview(p, iv);
+    ColDst cdst;
+    fill_coldst(p, cdst);
+    for (int t = 0; t < Sc; ++t) {
+        unsigned t0, t1, col0, wc;
+        chunk_bounds(p->ntiles, p->w, Sc, t, t0, t1, col0, wc);
+        if (t1 > t0) {
+            if (!p->fused) {
+                if (int rc = launch_cols(p, iv, cdst, p->ntiles, p->S, (unsigned) p->nx, p->n1, p->n2, p->two_level, &launches, nullptr)) return rc;
+            } else {
+                if (int rc = launch_cols_fused(p, iv, cdst, t0, t1 - t0)) return rc;
+                launches += 1;
+            }
+        }
+        CU(cudaEventRecord(evc[t], p->stream));
+        for (int k = 1; k < P; ++k) {
+            const int r = (me + k) % P;
+            cudaStream_t cs = p->pstream[r];
+            CU(cudaStreamWaitEvent(cs, evc[t], 0));
+            if (t == 0 && r == first_peer) CU(cudaEventRecord(evm[2], cs));
+            if (wc == 0) continue;
+            const cd *src = p->bufA + (unsigned long long) r * p->nxl * p->w + col0;
+            cd *dst = (cd *) p->peerV[r] + p->c0 + col0;
+            CU(cudaMemcpy2DAsync(dst, p->cy * sizeof(cd), src, (size_t) p->w * sizeof(cd), (size_t) wc * sizeof(cd), p->nxl,
+                                 cudaMemcpyDeviceToDevice, cs));
+        }
+    }
+    CU(cudaEventRecord(ev[3], p->stream));
+    for (int k = 1; k < P; ++k) {
+        const int q = (me + k) % P;
+        CU(cudaEventRecord(p->ev_peer[P + q], p->pstream[q]));
+        CU(cudaStreamWaitEvent(p->stream, p->ev_peer[P + q], 0));
+    }
+    CU(cudaEventRecord(evm[3], p->stream));
+    if (int rc = barrier_on_stream(p)) return rc;
+    CU(cudaEventRecord(ev[4], p->stream));
+    CU(cudaEventRecord(ev[5], p->stream));
+    p->launches = launches;
+    return 0;
+}
+
 int enqueue_transform(hpxfft_b200_plan *p)
 {
-    if (p->mode == MODE_P2P && p->P > 1 && !p->ipc_imported)
-        return fail(HPXFFT_B200_ESTATE, "p2p plan: hpxfft_b200_ipc_import has not been called");
-    if (p->P > 1 && p->mode != MODE_P2P && (p->chunks_r > 1 || p->chunks_c > 1)) return enqueue_transform_pipelined(p);
+    if (p->P > 1 && (p->transport == TR_FUSED || p->transport == TR_CE) && !p->ipc_imported)
+        return fail(HPXFFT_B200_ESTATE, "plan uses peer windows: hpxfft_b200_ipc_export / hpxfft_b200_ipc_import have not been called");
+    if (p->transport == TR_CE) return enqueue_transform_ce(p);
+    if (p->transport == TR_NCCL && (p->chunks_r > 1 || p->chunks_c > 1)) return enqueue_transform_nccl_pipelined(p);
     int launches = 0;
     RowDst rd;
     fill_rowdst(p, rd);
     ColDst cdst;
     fill_coldst(p, cdst);
     InterView iv;
-    iv.base = p->bufB;
-    iv.nxl = (unsigned) p->nxl;
-    iv.shift = pow2_shift(iv.nxl);
-    iv.tile_stride = (unsigned long long) (p->nxl + p->tile_pad_rows) * CW;
-    iv.rank_stride = (unsigned long long) p->ntiles * (p->nxl + p->tile_pad_rows) * CW;
+    fill_interview(p, iv);
 
-    cudaEvent_t *ev = p->evs.data() + (size_t) (p->nrec % hpxfft_b200_plan::EV_SETS) * hpxfft_b200_plan::EV_PER_SET;
+    cudaEvent_t *ev = event_set(p);
     p->nrec += 1;
     CU(cudaEventRecord(ev[0], p->stream));
     // phase 1: r2c rows (+ fused split / transpose)           -> first_fftw (first_split, first_trans fused)
     if (int rc = launch_rows(p, rd, (unsigned) p->nxl, (const cd *) p->V, (unsigned) p->cy, p->m)) return rc;
-    launches += 1 + (p->m > 16384 ? 1 : 0);
+    launches += rows_launch_count(p->m);
     CU(cudaEventRecord(ev[1], p->stream));
     // phase 2: exchange #1                                    -> first_comm
-    if (p->P > 1) {
-        if (p->mode == MODE_P2P) {
-            if (int rc = barrier_on_stream(p)) return rc;
-        } else if (int rc = exchange1(p))
-            return rc;
+    if (p->transport == TR_FUSED) {
+        if (int rc = barrier_on_stream(p)) return rc;
+    } else if (p->transport == TR_NCCL) {
+        if (int rc = exchange1_nccl(p)) return rc;
     }
     CU(cudaEventRecord(ev[2], p->stream));
     // phase 3: c2c columns (+ fused split / transpose)        -> second_fftw
@@ -813,18 +561,15 @@ int enqueue_transform(hpxfft_b200_plan *p)
         return rc;
     CU(cudaEventRecord(ev[3], p->stream));
     // phase 4: exchange #2                                    -> second_comm
-    if (p->P > 1) {
-        if (p->mode == MODE_P2P) {
-            if (int rc = barrier_on_stream(p)) return rc;
-        } else if (int rc = exchange2(p))
-            return rc;
+    if (p->transport == TR_FUSED) {
+        if (int rc = barrier_on_stream(p)) return rc;
+    } else if (p->transport == TR_NCCL) {
+        if (int rc = exchange2_nccl(p)) return rc;
     }
     CU(cudaEventRecord(ev[4], p->stream));
     // phase 5: unpack into the slab                           -> second_trans
-    if (p->P > 1 && p->mode != MODE_P2P) {
-        unpack_kernel<<<dim3((unsigned) p->nxl, (unsigned) p->P), 256, 0, p->stream>>>(p->bufB, (cd *) p->V, (unsigned) p->nxl,
-                                                                                      (unsigned) p->cy, p->wq0, (unsigned) p->P, (unsigned) p->rank);
-        CU(cudaGetLastError());
+    if (p->transport == TR_NCCL) {
+        if (int rc = launch_unpack(p, p->stream)) return rc;
         launches += 1;
     }
     CU(cudaEventRecord(ev[5], p->stream));
@@ -837,7 +582,8 @@ int read_timers(hpxfft_b200_plan *p)
     // averages over the executes enqueued since the last reset (at most the EV_SETS most recent)
     const long nset = p->nrec < hpxfft_b200_plan::EV_SETS ? p->nrec : hpxfft_b200_plan::EV_SETS;
     if (nset <= 0) return 0;
-    double acc[8] = {0};
+    const bool chunked = p->transport == TR_CE || (p->transport == TR_NCCL && (p->chunks_r > 1 || p->chunks_c > 1));
+    double acc[10] = {0};
     for (long sidx = 0; sidx < nset; ++sidx) {
         const long slot = ((p->nrec - 1 - sidx) % hpxfft_b200_plan::EV_SETS + hpxfft_b200_plan::EV_SETS) % hpxfft_b200_plan::EV_SETS;
         cudaEvent_t *ev = p->evs.data() + (size_t) slot * hpxfft_b200_plan::EV_PER_SET;
@@ -852,6 +598,13 @@ int read_timers(hpxfft_b200_plan *p)
         acc[6] += ms; // column level A (0 for single-level)
         CU(cudaEventElapsedTime(&ms, ev[6], ev[3]));
         acc[7] += ms; // column level B / single-level kernel
+        if (chunked) {
+            cudaEvent_t *evm = p->ev_comm.data() + (size_t) slot * 4;
+            CU(cudaEventElapsedTime(&ms, evm[0], evm[1]));
+            acc[8] += ms; // first copy of exchange #1 issued -> last one complete
+            CU(cudaEventElapsedTime(&ms, evm[2], evm[3]));
+            acc[9] += ms;
+        }
     }
     const double sc = 1e-3 / (double) nset;
     auto &m = p->meas;
@@ -868,8 +621,45 @@ int read_timers(hpxfft_b200_plan *p)
     m["cols_kernel"] = acc[2] * sc;
     m["cols_levelA_kernel"] = acc[6] * sc;
     m["cols_levelB_kernel"] = acc[7] * sc;
+    // span of the exchange traffic itself (chunked transports overlap it with the kernels); for the serial
+    // transports the span IS the exposed phase
+    m["first_comm_span"] = chunked ? acc[8] * sc : acc[1] * sc;
+    m["second_comm_span"] = chunked ? acc[9] * sc : acc[3] * sc;
     m["timer_samples"] = (double) nset;
     return 0;
+}
+
+// CPUs of the NUMA node the device hangs off (/sys/bus/pci/devices/<id>/local_cpulist)
+bool device_cpulist(int device, cpu_set_t *set)
+{
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    for (char *c = bus; *c; ++c) *c = (char) tolower(*c);
+    std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist");
+    std::string s;
+    if (!f || !std::getline(f, s) || s.empty()) return false;
+    CPU_ZERO(set);
+    int n = 0;
+    const char *c = s.c_str();
+    while (*c) {
+        char *e = nullptr;
+        long a = strtol(c, &e, 10), b = a;
+        if (e == c) break;
+        c = e;
+        if (*c == '-') {
+            b = strtol(c + 1, &e, 10);
+            c = e;
+        }
+        for (long i = a; i <= b && i < CPU_SETSIZE; ++i) {
+            CPU_SET((int) i, set);
+            ++n;
+        }
+        if (*c == ',') ++c;
+    }
+    return n > 0;
 }
 
 }  // namespace
@@ -880,7 +670,7 @@ int read_timers(hpxfft_b200_plan *p)
 extern "C" {
 
 int hpxfft_b200_version(void) { return HPXFFT_B200_VERSION; }
-const char *hpxfft_b200_last_error(void) { return g_err; }
+const char *hpxfft_b200_last_error(void) { return last_error_string(); }
 
 int hpxfft_b200_device_count(void)
 {
@@ -913,11 +703,30 @@ int hpxfft_b200_get_unique_id(void *id_out)
     return 0;
 }
 
+int hpxfft_b200_bind_host_to_device(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(HPXFFT_B200_ECUDA, "no CUDA device available (libhpxfft_b200 has no CPU fallback)");
+    }
+    if (device < 0) CU(cudaGetDevice(&device));
+    cpu_set_t set;
+    if (!device_cpulist(device, &set)) return fail(HPXFFT_B200_EINVAL, "no local_cpulist for device %d", device);
+    if (sched_setaffinity(0, sizeof(set), &set) != 0) return fail(HPXFFT_B200_EINVAL, "sched_setaffinity failed for device %d", device);
+    return 0;
+}
+
 void hpxfft_b200_destroy(hpxfft_b200_plan *p)
 {
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
+    for (auto &s : p->pstream)
+        if (s) {
+            cudaStreamSynchronize(s);
+            cudaStreamDestroy(s);
+        }
     if (p->ipc_imported) {
         for (int q = 0; q < p->P; ++q) {
             if (q == p->rank) continue;
@@ -926,8 +735,9 @@ void hpxfft_b200_destroy(hpxfft_b200_plan *p)
         }
     }
     if (p->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(p->comm);
-    for (auto &e : p->ev_chunk)
-        if (e) cudaEventDestroy(e);
+    for (auto *vec : {&p->ev_chunk, &p->ev_peer, &p->ev_comm, &p->evs})
+        for (auto &e : *vec)
+            if (e) cudaEventDestroy(e);
     if (p->cstream) {
         cudaStreamSynchronize(p->cstream);
         cudaStreamDestroy(p->cstream);
@@ -943,8 +753,6 @@ void hpxfft_b200_destroy(hpxfft_b200_plan *p)
     cudaFree(p->tw_col);
     cudaFree(p->tw_il);
     cudaFree(p->d_barrier);
-    for (auto &e : p->evs)
-        if (e) cudaEventDestroy(e);
     for (auto &e : p->ev_io)
         if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -980,6 +788,20 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     p->device = device;
     p->mode = mode;
     p->plan_flag = plan_flag;
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    // transport of the slab exchanges
+    if (nranks == 1)
+        p->transport = TR_NONE;
+    else if (mode == MODE_P2P)
+        p->transport = TR_FUSED;
+    else if (mode == MODE_SCATTER)
+        p->transport = TR_NCCL;
+    else {
+        const char *e = getenv("HPXFFT_B200_A2A");
+        if (e && !strcmp(e, "nccl")) p->transport = TR_NCCL;
+        else if (e && !strcmp(e, "fused")) p->transport = TR_FUSED;
+        else p->transport = TR_CE;
+    }
     // dimension inference: core/src/shared/loop.cpp:163-165, core/src/distributed/loop.cpp:284-287
     p->nxl = n_x_local;
     p->n_col = n_col;
@@ -1036,50 +858,20 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
 
     // buffers
     const size_t bytesV = p->nxl * p->n_col * sizeof(double);
-    if (nranks == 1) {
-        if (const char *e = getenv("HPXFFT_B200_TILE_PAD")) { int v = atoi(e); if (v > 0 && v <= 4096) p->tile_pad_rows = (size_t) v; }
-    }
-    p->bytesB = (size_t) p->ntiles * (p->nx + p->tile_pad_rows) * CW * sizeof(cd); // I: [r][ct][j][c], also >= nxl*cy for exchange #2
+    p->bytesB = (size_t) p->ntiles * p->nx * CW * sizeof(cd); // I: [r][ct][j][c], also >= nxl*cy for exchange #2
     if (p->bytesB < p->nxl * p->cy * sizeof(cd)) p->bytesB = p->nxl * p->cy * sizeof(cd);
     p->bytesS = p->two_level ? (size_t) p->ntiles * p->nx * CW * sizeof(cd) : 0;
     if (p->two_level) {
         const char *e = getenv("HPXFFT_B200_FUSED");
-        p->fused = !(e && e[0] == '0');
-        p->fused_tma = p->fused && (e && e[0] == '2'); // HPXFFT_B200_FUSED=2 selects the TMA-bulk/mbarrier variant
-        // N = 512 tiles need 2 x 128 KB with a staging buffer: fall back to the plain fused kernel
-        if (p->n2 < 32) p->fused_tma = false; // single-pass tiles have no shared-memory buffer to refill
+        p->fused = !(e && e[0] == '0') && fused_pair_exists(p->n1, p->n2);
     }
-    if (nranks > 1 && mode != MODE_P2P) {
-        // Sub-slab pipelining of the NCCL exchanges is implemented and parity-tested but OFF by default:
-        // NCCL's copy kernels need >= 32 CTAs for full NVLink rate, which the persistent FFT kernels
-        // cannot spare without losing more than the overlap wins.
-        int want = 1;
-        if (const char *e = getenv("HPXFFT_B200_CHUNKS")) want = atoi(e) > 0 ? atoi(e) : 1;
-        if (want > 1) {
-            p->sm_reserve = 16;
-            if (const char *e = getenv("HPXFFT_B200_SM_RESERVE")) { int v = atoi(e); if (v >= 0 && v <= 64) p->sm_reserve = v; }
-        }
-    }
-    if (p->fused) {
-        int bps = 1, sms = 148;
-        if (int rc = fused_blocks_per_sm(p->n1, p->n2, &bps, p->fused_tma)) return bail(rc);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        if (const char *e = getenv("HPXFFT_B200_FUSED_BPS")) { int v = atoi(e); if (v >= 1 && v < bps) bps = v; }
-        p->fused_grid = (unsigned) (bps * (sms - p->sm_reserve));
-        const unsigned per_group = p->n1 + p->n2;
-        p->lag = (unsigned) ((3 * (size_t) p->fused_grid / 2 + per_group - 1) / per_group) + 1;
-        if (const char *e = getenv("HPXFFT_B200_LAG")) { int v = atoi(e); if (v >= 1) p->lag = (unsigned) v; }
-        p->nslot = 2 * p->lag + 1;
-        if (const char *e = getenv("HPXFFT_B200_NSLOT")) { int v = atoi(e); if (v > (int) p->lag) p->nslot = (unsigned) v; }
-        if (p->nslot > p->ntiles) p->nslot = p->ntiles > 0 ? p->ntiles : 1;
-        p->bytesS = (size_t) p->nslot * p->nx * CW * sizeof(cd);
-    }
-    if (nranks > 1 && mode != MODE_P2P) {
-        size_t tiles_all = 0;
-        for (int q = 0; q < nranks; ++q) tiles_all += p->ntiles_of[q];
-        p->bytesA = tiles_all * p->nxl * CW * sizeof(cd);
-        const size_t ex2 = (size_t) nranks * p->nxl * p->w * sizeof(cd);
-        if (p->bytesA < ex2) p->bytesA = ex2;
+    const bool nccl_pipelined = p->transport == TR_NCCL && mode == MODE_ALL_TO_ALL && env_int("HPXFFT_B200_CHUNKS", 1) > 1;
+    if (nccl_pipelined) {
+        // Sub-slab pipelining of the NCCL exchanges is OFF unless asked for: NCCL's copy kernels need >= 32 CTAs
+        // for full NVLink rate, which the persistent FFT kernels cannot spare.
+        p->sm_reserve = 16;
+        const int v = env_int("HPXFFT_B200_SM_RESERVE", 16);
+        if (v >= 0 && v <= 64) p->sm_reserve = v;
     }
 #define CUB(call)                                                                                     \
     do {                                                                                              \
@@ -1087,6 +879,35 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         if (e_ != cudaSuccess)                                                                        \
             return bail(fail(HPXFFT_B200_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)));     \
     } while (0)
+    if (p->fused) {
+        int bps = 1;
+        if (int rc = fused_blocks_per_sm(p->n1, p->n2, &bps)) return bail(rc);
+        {
+            const int v = env_int("HPXFFT_B200_FUSED_BPS", 0);
+            if (v >= 1 && v < bps) bps = v;
+        }
+        p->fused_grid = (unsigned) (bps * (p->sm_count - p->sm_reserve));
+        const unsigned per_group = p->n1 + p->n2;
+        p->lag = (unsigned) ((3 * (size_t) p->fused_grid / 2 + per_group - 1) / per_group) + 1;
+        {
+            const int v = env_int("HPXFFT_B200_LAG", 0);
+            if (v >= 1) p->lag = (unsigned) v;
+        }
+        p->nslot = 2 * p->lag + 1;
+        {
+            const int v = env_int("HPXFFT_B200_NSLOT", 0);
+            if (v > (int) p->lag) p->nslot = (unsigned) v;
+        }
+        if (p->nslot > p->ntiles) p->nslot = p->ntiles > 0 ? p->ntiles : 1;
+        p->bytesS = (size_t) p->nslot * p->nx * CW * sizeof(cd);
+    }
+    if (p->transport == TR_NCCL || p->transport == TR_CE) {
+        size_t tiles_all = 0;
+        for (int q = 0; q < nranks; ++q) tiles_all += p->ntiles_of[q];
+        p->bytesA = tiles_all * p->nxl * CW * sizeof(cd);
+        const size_t ex2 = (size_t) nranks * p->nxl * p->w * sizeof(cd);
+        if (p->bytesA < ex2) p->bytesA = ex2;
+    }
     CUB(cudaMalloc(&p->V, bytesV));
     CUB(cudaMalloc(&p->bufB, p->bytesB));
     if (p->m > 16384) CUB(cudaMalloc(&p->zraw, p->nxl * p->m * sizeof(cd)));
@@ -1116,22 +937,31 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         }
     }
 
-    if (nranks > 1 && mode != MODE_P2P) {
-        int want = 1;
-        if (const char *e = getenv("HPXFFT_B200_CHUNKS")) want = atoi(e) > 0 ? atoi(e) : 1;
-        int sr = want, sc = want;
+    // sub-slab chunks (rank-invariant: derived from quantities every rank computes identically)
+    if (p->transport == TR_CE || nccl_pipelined) {
+        const int want = env_int("HPXFFT_B200_CHUNKS", p->transport == TR_CE ? 4 : 1);
+        int sr = want < 1 ? 1 : want, sc = sr;
         while (sr > 1 && (p->nxl % sr != 0 || p->nxl / sr < 8)) sr /= 2;
         if (!p->fused) sc = 1;
-        while (sc > 1 && p->ntiles / sc < 2 * (p->lag + 1)) sc /= 2;
+        unsigned min_tiles = p->ntiles_of[0]; // every rank but the last owns ntiles_of[0] strips; the last one at least as many
+        while (sc > 1 && min_tiles / sc < 2 * (p->lag + 1)) sc /= 2;
         p->chunks_r = sr < 1 ? 1 : sr;
         p->chunks_c = sc < 1 ? 1 : sc;
-        if (p->chunks_r > 1 || p->chunks_c > 1) {
+        p->ev_chunk.assign((size_t) p->chunks_r + p->chunks_c, nullptr);
+        for (auto &e : p->ev_chunk) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p->ev_comm.assign((size_t) hpxfft_b200_plan::EV_SETS * 4, nullptr);
+        for (auto &e : p->ev_comm) CUB(cudaEventCreate(&e));
+        p->ev_peer.assign(2 * (size_t) nranks, nullptr);
+        for (auto &e : p->ev_peer) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (p->transport == TR_CE) {
+            p->pstream.assign(nranks, nullptr);
+            for (int q = 0; q < nranks; ++q)
+                if (q != rank) CUB(cudaStreamCreateWithPriority(&p->pstream[q], cudaStreamNonBlocking, hi));
+        } else {
             CUB(cudaMalloc(&p->bufC, p->nxl * p->cy * sizeof(cd)));
-            int lo = 0, hi = 0;
-            cudaDeviceGetStreamPriorityRange(&lo, &hi);
             CUB(cudaStreamCreateWithPriority(&p->cstream, cudaStreamNonBlocking, hi));
-            p->ev_chunk.assign((size_t) p->chunks_r + p->chunks_c + 2, nullptr);
-            for (auto &e : p->ev_chunk) CUB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
     }
     if (nranks > 1) {
@@ -1165,9 +995,9 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     const double N = (double) p->nx * (double) p->ny;
     p->meas["plan_flops"] = 2.5 * N * std::log2(N > 1 ? N : 2);
 
-    char buf[256];
+    char buf[320];
     snprintf(buf, sizeof(buf), "r2c rows: n=%zu via half-length complex Stockham m=%zu (%s), %d points/thread, paired radix-16 last pass + Hermitian split",
-             p->ny, p->m, p->m <= 16 ? "register-resident" : "shared-memory pencil", p->m <= 16 ? (int) p->m : ROW_PT);
+             p->ny, p->m, p->m <= 16 ? "register-resident" : "shared-memory pencil", p->m <= 16 ? (int) p->m : 32);
     p->row_desc = buf;
     if (p->rows_generic) p->row_desc = "r2c rows: direct DFT (length is not a power of two)";
     if (p->cols_generic)
@@ -1175,7 +1005,6 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     else if (p->two_level)
         snprintf(buf, sizeof(buf), "c2c columns: n=%zu four-step %u x %u on %d-column tiles (level A strided + twiddle, level B contiguous)%s",
                  p->nx, p->n1, p->n2, CW, p->fused ? ", fused persistent launch with L2-resident scratch ring" : "");
-    if (p->fused_tma) p->col_desc_extra = " [producer warp: cp.async.bulk + mbarrier]";
     else
         snprintf(buf, sizeof(buf), "c2c columns: n=%zu single Stockham tile FFT on %d-column tiles", p->nx, CW);
     p->col_desc = buf;
@@ -1183,13 +1012,16 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     return 0;
 }
 
-int hpxfft_b200_ipc_count(const hpxfft_b200_plan *p) { return (p && p->mode == MODE_P2P) ? 2 : 0; }
+int hpxfft_b200_ipc_count(const hpxfft_b200_plan *p)
+{
+    return (p && p->P > 1 && (p->transport == TR_FUSED || p->transport == TR_CE)) ? 2 : 0;
+}
 
 int hpxfft_b200_ipc_export(hpxfft_b200_plan *p, void *handles_out)
 {
     static_assert(sizeof(cudaIpcMemHandle_t) == HPXFFT_B200_IPC_HANDLE_BYTES, "ipc handle size");
     if (!p || !handles_out) return fail(HPXFFT_B200_EINVAL, "NULL argument");
-    if (p->mode != MODE_P2P) return fail(HPXFFT_B200_ESTATE, "not a p2p plan");
+    if (hpxfft_b200_ipc_count(p) == 0) return fail(HPXFFT_B200_ESTATE, "this plan exports no peer windows");
     CU(cudaSetDevice(p->device));
     cudaIpcMemHandle_t h[2];
     CU(cudaIpcGetMemHandle(&h[0], p->bufB));
@@ -1201,7 +1033,7 @@ int hpxfft_b200_ipc_export(hpxfft_b200_plan *p, void *handles_out)
 int hpxfft_b200_ipc_import(hpxfft_b200_plan *p, const void *all_handles)
 {
     if (!p || !all_handles) return fail(HPXFFT_B200_EINVAL, "NULL argument");
-    if (p->mode != MODE_P2P) return fail(HPXFFT_B200_ESTATE, "not a p2p plan");
+    if (hpxfft_b200_ipc_count(p) == 0) return fail(HPXFFT_B200_ESTATE, "this plan uses no peer windows");
     CU(cudaSetDevice(p->device));
     const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *) all_handles;
     for (int q = 0; q < p->P; ++q) {
@@ -1217,13 +1049,24 @@ int hpxfft_b200_ipc_import(hpxfft_b200_plan *p, const void *all_handles)
     return 0;
 }
 
+const char *hpxfft_b200_transport(const hpxfft_b200_plan *p)
+{
+    if (!p) return "";
+    switch (p->transport) {
+    case TR_NCCL: return p->mode == MODE_SCATTER ? "nccl-rooted" : ((p->chunks_r > 1 || p->chunks_c > 1) ? "nccl-pipelined" : "nccl");
+    case TR_CE: return "copy-engine";
+    case TR_FUSED: return "fused-peer-store";
+    default: return "none";
+    }
+}
+
 int hpxfft_b200_upload(hpxfft_b200_plan *p, const double *host_slab)
 {
     if (!p || !host_slab) return fail(HPXFFT_B200_EINVAL, "NULL argument");
     CU(cudaSetDevice(p->device));
     cudaEvent_t a = p->ev_io[0], b = p->ev_io[1];
     CU(cudaEventRecord(a, p->stream));
-    CU(cudaMemcpyAsync(p->V, host_slab, p->nxl * p->n_col * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(p->V, host_slab, p->nxl * p->n_col * sizeof(double), cudaMemcpyDefault, p->stream));
     CU(cudaEventRecord(b, p->stream));
     CU(cudaStreamSynchronize(p->stream));
     float ms = 0;
@@ -1238,7 +1081,7 @@ int hpxfft_b200_download(hpxfft_b200_plan *p, double *host_slab)
     CU(cudaSetDevice(p->device));
     cudaEvent_t a = p->ev_io[0], b = p->ev_io[1];
     CU(cudaEventRecord(a, p->stream));
-    CU(cudaMemcpyAsync(host_slab, p->V, p->nxl * p->n_col * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(host_slab, p->V, p->nxl * p->n_col * sizeof(double), cudaMemcpyDefault, p->stream));
     CU(cudaEventRecord(b, p->stream));
     CU(cudaStreamSynchronize(p->stream));
     float ms = 0;
@@ -1247,14 +1090,24 @@ int hpxfft_b200_download(hpxfft_b200_plan *p, double *host_slab)
     return 0;
 }
 
+int hpxfft_b200_download_tile(hpxfft_b200_plan *p, size_t row0, size_t nrows, size_t col0, size_t ncols, double *host_out)
+{
+    if (!p || !host_out) return fail(HPXFFT_B200_EINVAL, "NULL argument");
+    if (row0 + nrows > p->nxl || col0 + ncols > p->n_col || nrows == 0 || ncols == 0)
+        return fail(HPXFFT_B200_EINVAL, "tile [%zu+%zu) x [%zu+%zu) outside the %zu x %zu slab", row0, nrows, col0, ncols, p->nxl, p->n_col);
+    CU(cudaSetDevice(p->device));
+    CU(cudaMemcpy2DAsync(host_out, ncols * sizeof(double), p->V + row0 * p->n_col + col0, p->n_col * sizeof(double), ncols * sizeof(double),
+                         nrows, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
 int hpxfft_b200_fill(hpxfft_b200_plan *p, int pattern, uint64_t seed)
 {
     if (!p) return fail(HPXFFT_B200_EINVAL, "NULL plan");
     if (pattern < 0 || pattern > 2) return fail(HPXFFT_B200_EINVAL, "unknown pattern %d", pattern);
     CU(cudaSetDevice(p->device));
-    fill_kernel<<<148 * 8, 256, 0, p->stream>>>(p->V, (unsigned) p->nxl, (unsigned) p->ny, (unsigned) p->n_col,
-                                               (unsigned long long) p->rank * p->nxl, pattern, seed);
-    CU(cudaGetLastError());
+    if (int rc = launch_fill(p, pattern, seed)) return rc;
     CU(cudaStreamSynchronize(p->stream));
     return 0;
 }
@@ -1316,6 +1169,48 @@ int hpxfft_b200_transform_async(hpxfft_b200_plan *p, double *host_slab_inout)
     return 0;
 }
 
+int hpxfft_b200_bench_exchange(hpxfft_b200_plan *p, int which, int reps, double *ms_out)
+{
+    if (!p || !ms_out || reps < 1 || (which != 1 && which != 2)) return fail(HPXFFT_B200_EINVAL, "bad arguments");
+    if (p->transport != TR_NCCL && p->transport != TR_CE) return fail(HPXFFT_B200_ESTATE, "transport %s has no separable exchange", hpxfft_b200_transport(p));
+    if (p->transport == TR_CE && !p->ipc_imported) return fail(HPXFFT_B200_ESTATE, "peer windows not imported");
+    CU(cudaSetDevice(p->device));
+    const int P = p->P, me = p->rank;
+    std::vector<unsigned long long> soff(P + 1, 0);
+    for (int q = 0; q < P; ++q) soff[q + 1] = soff[q] + iblock(p, q);
+    cudaEvent_t a = p->ev_io[0], b = p->ev_io[1];
+    auto once = [&]() -> int {
+        if (p->transport == TR_NCCL) return which == 1 ? exchange1_nccl(p) : exchange2_nccl(p);
+        CU(cudaEventRecord(p->ev_chunk[0], p->stream));
+        for (int k = 1; k < P; ++k) {
+            const int q = (me + k) % P;
+            cudaStream_t cs = p->pstream[q];
+            CU(cudaStreamWaitEvent(cs, p->ev_chunk[0], 0));
+            if (which == 1)
+                CU(cudaMemcpyAsync((cd *) p->peerI[q] + (unsigned long long) me * iblock(p, q), p->bufA + soff[q], iblock(p, q) * sizeof(cd),
+                                   cudaMemcpyDeviceToDevice, cs));
+            else
+                CU(cudaMemcpy2DAsync((cd *) p->peerV[q] + p->c0, p->cy * sizeof(cd), p->bufA + (unsigned long long) q * p->nxl * p->w,
+                                     (size_t) p->w * sizeof(cd), (size_t) p->w * sizeof(cd), p->nxl, cudaMemcpyDeviceToDevice, cs));
+            CU(cudaEventRecord(p->ev_peer[q], cs));
+            CU(cudaStreamWaitEvent(p->stream, p->ev_peer[q], 0));
+        }
+        return barrier_on_stream(p);
+    };
+    if (int rc = once()) return rc; // warm-up
+    if (p->transport == TR_CE)
+        if (int rc = barrier_on_stream(p)) return rc;
+    CU(cudaEventRecord(a, p->stream));
+    for (int i = 0; i < reps; ++i)
+        if (int rc = once()) return rc;
+    CU(cudaEventRecord(b, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    *ms_out = (double) ms / reps;
+    return 0;
+}
+
 double hpxfft_b200_measurement(const hpxfft_b200_plan *p, const char *key)
 {
     if (!p || !key) return 0.0;
@@ -1330,7 +1225,7 @@ int hpxfft_b200_write_plans(const hpxfft_b200_plan *p, const char *file_path)
     if (!f) return fail(HPXFFT_B200_EINVAL, "Failed to open file: %s", file_path);
     // same two-section structure as core/src/shared/loop.cpp:203-209
     fprintf(f, "FFTW r2c 1D plan:\n(hpxfft_b200 sm_100a %s)\n", p->row_desc.c_str());
-    fprintf(f, "FFTW c2c 1D plan:\n(hpxfft_b200 sm_100a %s%s)\n\n", p->col_desc.c_str(), p->col_desc_extra.c_str());
+    fprintf(f, "FFTW c2c 1D plan:\n(hpxfft_b200 sm_100a %s)\n\n", p->col_desc.c_str());
     fclose(f);
     return 0;
 }
@@ -1341,8 +1236,8 @@ int hpxfft_b200_launches_per_execute(const hpxfft_b200_plan *p)
 {
     if (!p) return 0;
     if (p->launches > 0) return p->launches; // counted by the last execute
-    int n = 1 + ((p->two_level && !p->fused) ? 2 : 1) + (p->m > 16384 ? 1 : 0);
-    if (p->P > 1 && p->mode != MODE_P2P) n += 1;
+    int n = rows_launch_count(p->m) + ((p->two_level && !p->fused) ? 2 : 1);
+    if (p->transport == TR_NCCL) n += 1;
     return n;
 }
 
@@ -1379,6 +1274,7 @@ int hpxfft_b200_r2c_rows(double *host_rows, size_t batch, size_t n_col, int devi
     hpxfft_b200_plan P;
     hpxfft_b200_plan *p = &P;
     p->device = device;
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
     p->nxl = batch;
     p->cy = cy;
     p->ntiles = (unsigned) ((cy + CW - 1) / CW);
@@ -1421,15 +1317,20 @@ int hpxfft_b200_r2c_rows(double *host_rows, size_t batch, size_t n_col, int devi
         cleanup();
         return rc;
     }
-    untile_kernel<<<148 * 4, 256, 0, p->stream>>>(p->bufB, (cd *) p->V, (unsigned) batch, (unsigned) cy);
-    CUR(cudaGetLastError());
+    rc = launch_untile(p->bufB, (cd *) p->V, (unsigned) batch, (unsigned) cy, p->stream);
+    if (rc) {
+        cleanup();
+        return rc;
+    }
     CUR(cudaMemcpyAsync(host_rows, p->V, bytes, cudaMemcpyDeviceToHost, p->stream));
     CUR(cudaStreamSynchronize(p->stream));
     cleanup();
     return 0;
 }
 
-int hpxfft_b200_c2c_cols(double *host_data, size_t n, size_t width, int device)
+// variant: 0 = the kernels a plan of this length runs (fused persistent four-step when n > 256),
+//          1 = the unfused kernels (single tile / level A + level B launches)
+int hpxfft_b200_c2c_cols_variant(double *host_data, size_t n, size_t width, int device, int variant)
 {
     if (!host_data || n == 0 || width == 0) return fail(HPXFFT_B200_EINVAL, "bad arguments");
     // a plan with nx = n rows and cy = width complex columns (n_col = 2*width); ny is irrelevant here,
@@ -1445,11 +1346,13 @@ int hpxfft_b200_c2c_cols(double *host_data, size_t n, size_t width, int device)
     hpxfft_b200_plan P;
     hpxfft_b200_plan *p = &P;
     p->device = device;
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
     p->nxl = p->nx = n;
     p->cy = width;
     p->w = (unsigned) width;
     p->ntiles = (unsigned) ((width + CW - 1) / CW);
     choose_col_split(n, p->n1, p->n2, p->two_level);
+    p->fused = variant == 0 && p->two_level && fused_pair_exists(p->n1, p->n2);
     const size_t bytes = n * width * sizeof(cd), tbytes = (size_t) p->ntiles * n * CW * sizeof(cd);
     cd *A = nullptr;
     std::vector<double2> t;
@@ -1459,10 +1362,11 @@ int hpxfft_b200_c2c_cols(double *host_data, size_t n, size_t width, int device)
         cudaFree(A);
         cudaFree(p->bufB);
         cudaFree(p->S);
+        cudaFree(p->ctl);
         cudaFree(p->tw_col);
         cudaFree(p->tw_il);
         if (p->stream) cudaStreamDestroy(p->stream);
-        p->bufB = nullptr; p->S = nullptr; p->tw_col = nullptr; p->tw_il = nullptr; p->stream = nullptr;
+        p->bufB = nullptr; p->S = nullptr; p->ctl = nullptr; p->tw_col = nullptr; p->tw_il = nullptr; p->stream = nullptr;
     };
 #define CUC(call)                                                                                        \
     do {                                                                                                 \
@@ -1476,7 +1380,22 @@ int hpxfft_b200_c2c_cols(double *host_data, size_t n, size_t width, int device)
     CUC(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CUC(cudaMalloc(&A, bytes));
     CUC(cudaMalloc(&p->bufB, tbytes));
-    if (p->two_level) CUC(cudaMalloc(&p->S, tbytes));
+    size_t sbytes = tbytes;
+    if (p->fused) {
+        int bps = 1;
+        if ((rc = fused_blocks_per_sm(p->n1, p->n2, &bps))) {
+            cleanup();
+            return rc;
+        }
+        p->fused_grid = (unsigned) (bps * p->sm_count);
+        const unsigned per_group = p->n1 + p->n2;
+        p->lag = (unsigned) ((3 * (size_t) p->fused_grid / 2 + per_group - 1) / per_group) + 1;
+        p->nslot = 2 * p->lag + 1;
+        if (p->nslot > p->ntiles) p->nslot = p->ntiles;
+        sbytes = (size_t) p->nslot * n * CW * sizeof(cd);
+        CUC(cudaMalloc(&p->ctl, (1 + 2 * (size_t) p->ntiles) * sizeof(unsigned)));
+    }
+    if (p->two_level) CUC(cudaMalloc(&p->S, sbytes));
     CUC(cudaMalloc(&p->tw_col, t.size() * sizeof(double2)));
     CUC(cudaMemcpyAsync(p->tw_col, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
     std::vector<double2> w2;
@@ -1486,8 +1405,10 @@ int hpxfft_b200_c2c_cols(double *host_data, size_t n, size_t width, int device)
         CUC(cudaMemcpyAsync(p->tw_il, w2.data(), w2.size() * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
     }
     CUC(cudaMemcpyAsync(A, host_data, bytes, cudaMemcpyHostToDevice, p->stream));
-    tile_kernel<<<148 * 4, 256, 0, p->stream>>>(A, p->bufB, (unsigned) n, (unsigned) width);
-    CUC(cudaGetLastError());
+    if ((rc = launch_tile(A, p->bufB, (unsigned) n, (unsigned) width, p->stream))) {
+        cleanup();
+        return rc;
+    }
     InterView iv;
     iv.base = p->bufB;
     iv.nxl = (unsigned) n;
@@ -1501,7 +1422,10 @@ int hpxfft_b200_c2c_cols(double *host_data, size_t n, size_t width, int device)
     cdst.base[0] = A;
     cdst.pitch[0] = (unsigned) width;
     cdst.col0[0] = 0;
-    rc = launch_cols(p, iv, cdst, p->ntiles, p->S, (unsigned) n, p->n1, p->n2, p->two_level, nullptr);
+    if (p->fused)
+        rc = launch_cols_fused(p, iv, cdst, 0u, p->ntiles);
+    else
+        rc = launch_cols(p, iv, cdst, p->ntiles, p->S, (unsigned) n, p->n1, p->n2, p->two_level, nullptr);
     if (rc) {
         cleanup();
         return rc;
@@ -1510,6 +1434,11 @@ int hpxfft_b200_c2c_cols(double *host_data, size_t n, size_t width, int device)
     CUC(cudaStreamSynchronize(p->stream));
     cleanup();
     return 0;
+}
+
+int hpxfft_b200_c2c_cols(double *host_data, size_t n, size_t width, int device)
+{
+    return hpxfft_b200_c2c_cols_variant(host_data, n, width, device, 0);
 }
 
 }  // extern "C"

@@ -81,8 +81,8 @@ class loop:
             uid = b.broadcast_bytes(raw, 0)
         capi.check(self._lib.hpxfft_b200_create(C.byref(self._plan), values_vec.n_row(), values_vec.n_col(), b.rank, b.size,
                                                 self._device, COMM_FLAG.encode(), PLAN_FLAG.encode(), uid))
-        if COMM_FLAG == "p2p" and b.size > 1:
-            cnt = self._lib.hpxfft_b200_ipc_count(self._plan)
+        cnt = self._lib.hpxfft_b200_ipc_count(self._plan)  # peer windows (copy-engine / fused transports)
+        if cnt > 0:
             buf = C.create_string_buffer(cnt * capi.IPC_HANDLE_BYTES)
             capi.check(self._lib.hpxfft_b200_ipc_export(self._plan, buf))
             allh = b"".join(b.all_gather_bytes(buf.raw))

@@ -53,9 +53,9 @@ struct loop
         hpxfft::util::b200_check(hpxfft_b200_create(&plan_, values_vec_.n_row(), values_vec_.n_col(), rank, nranks,
                                                    device_ >= 0 ? device_ : boot_.local_device(), COMM_FLAG.c_str(),
                                                    PLAN_FLAG.c_str(), nranks > 1 ? uid.data() : nullptr));
-        if (COMM_FLAG == "p2p" && nranks > 1)
+        if (const int cnt = hpxfft_b200_ipc_count(plan_); cnt > 0)  // peer windows (copy-engine / fused transports)
         {
-            std::string mine(static_cast<std::size_t>(hpxfft_b200_ipc_count(plan_)) * HPXFFT_B200_IPC_HANDLE_BYTES, '\0');
+            std::string mine(static_cast<std::size_t>(cnt) * HPXFFT_B200_IPC_HANDLE_BYTES, '\0');
             hpxfft::util::b200_check(hpxfft_b200_ipc_export(plan_, &mine[0]));
             std::string all;
             for (const auto &s : boot_.all_gather("ipc", mine)) all += s;

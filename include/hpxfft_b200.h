@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HPXFFT_B200_VERSION 100
+#define HPXFFT_B200_VERSION 200
 
 #define HPXFFT_B200_OK 0
 #define HPXFFT_B200_EINVAL (-1)     /* bad argument / unsupported size                          */
@@ -81,23 +81,50 @@ int hpxfft_b200_partition(size_t cy, int nranks, int rank, size_t *c0, size_t *w
  *   rank, nranks : this locality / number of localities (hpx::get_locality_id / get_num_localities)
  *   device    : CUDA device ordinal for this rank, or -1 for the current device
  *   comm_flag : NULL (shared::loop, nranks must be 1) | "scatter" | "all_to_all"   (reference modes,
- *               distributed/loop.cpp:156-179) | "p2p" (fused peer-store variant, extension)
+ *               distributed/loop.cpp:156-179) | "p2p" (fused peer-store variant, extension).
+ *               "scatter"    = P rooted scatters, one NCCL send/recv group per root, issued in root order
+ *                              (scatter_to / scatter_from on P communicators, distributed/loop.cpp:39-69,158-167);
+ *               "all_to_all" = one personalised all-to-all per exchange (distributed/loop.cpp:72-84).  Its
+ *                              transport is chosen by the environment variable HPXFFT_B200_A2A:
+ *                              "ce" (default)  copy-engine peer copies over the IPC windows, cut into sub-slab
+ *                                              chunks that overlap the FFT kernels, landing exchange #2
+ *                                              directly in the destination slab;
+ *                              "nccl"          one grouped ncclSend/ncclRecv exchange + unpack kernel;
+ *                              "fused"         same as "p2p";
+ *               "p2p"        = the FFT kernels store straight into the owners' windows over NVLink.
+ *               Plans whose hpxfft_b200_ipc_count() is non-zero need the export / all-gather / import
+ *               handshake below before the first execute.
  *   plan_flag : "estimate" | "measure" | "patient" | "exhaustive"  (util/adapter_fftw.hpp:22-44)
  *   unique_id : HPXFFT_B200_UNIQUE_ID_BYTES from rank 0's hpxfft_b200_get_unique_id; may be NULL
  *               when nranks == 1 */
 int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, int rank, int nranks,
                        int device, const char *comm_flag, const char *plan_flag, const void *unique_id);
 
-/* "p2p" mode only: export this rank's receive-window handles (count * HPXFFT_B200_IPC_HANDLE_BYTES,
- * count = hpxfft_b200_ipc_count()), all-gather them in rank order, import on every rank. */
+/* Peer windows (copy-engine and fused transports): export this rank's receive-window handles
+ * (count * HPXFFT_B200_IPC_HANDLE_BYTES, count = hpxfft_b200_ipc_count(); 0 = nothing to do), all-gather
+ * them in rank order, import on every rank.  Replaces the per-exchange buffers HPX serialises
+ * (core/src/distributed/loop.cpp:51,75). */
 int hpxfft_b200_ipc_count(const hpxfft_b200_plan *);
 int hpxfft_b200_ipc_export(hpxfft_b200_plan *, void *handles_out);
 int hpxfft_b200_ipc_import(hpxfft_b200_plan *, const void *all_handles /* nranks * count * 64 B */);
+
+/* name of the exchange transport the plan settled on: "none", "nccl", "nccl-rooted", "nccl-pipelined",
+ * "copy-engine", "fused-peer-store" */
+const char *hpxfft_b200_transport(const hpxfft_b200_plan *);
+/* Pins the calling thread (and what it allocates by first touch, e.g. the page-locked vector_2d storage) to
+ * the CPUs of the NUMA node the device hangs off, so that host<->device copies of all ranks of a node do
+ * not funnel through one socket.  device = -1: current device. */
+int hpxfft_b200_bind_host_to_device(int device);
 
 /* Host <-> device staging of the slab (the by-value vector_2d hand-over of initialize /
  * "return std::move(values_vec_)", core/src/shared/loop.cpp:161,112). */
 int hpxfft_b200_upload(hpxfft_b200_plan *, const double *host_slab);
 int hpxfft_b200_download(hpxfft_b200_plan *, double *host_slab);
+/* host_slab may also be a DEVICE pointer (unified addressing): the copy is then device-to-device and the
+ * caller keeps its data on the GPU (initialize from device memory, no PCIe).
+ * download_tile copies the sub-block rows [row0, row0+nrows) x doubles [col0, col0+ncols) into a dense host
+ * array -- sampled checks of slabs that are too large to bring back whole. */
+int hpxfft_b200_download_tile(hpxfft_b200_plan *, size_t row0, size_t nrows, size_t col0, size_t ncols, double *host_out);
 /* on-device synthetic input (no PCIe); row index is global: rank*n_x_local + i */
 int hpxfft_b200_fill(hpxfft_b200_plan *, int pattern, uint64_t seed);
 
@@ -119,10 +146,15 @@ int hpxfft_b200_transform(hpxfft_b200_plan *, double *host_slab_inout);
  * directions: the download of transform i overlaps the upload of transform i+1. */
 int hpxfft_b200_transform_async(hpxfft_b200_plan *, double *host_slab_inout);
 
+/* Runs exchange #1 or #2 (which = 1 | 2) ALONE `reps` times on whatever the staging buffers hold and
+ * returns the average milliseconds -- the NVLink roofline of the transport without the FFT kernels.
+ * Collective; the slab contents are undefined afterwards.  HPXFFT_B200_ESTATE for the fused transport. */
+int hpxfft_b200_bench_exchange(hpxfft_b200_plan *, int which, int reps, double *ms_out);
+
 /* Replaces loop::get_measurement (core/src/shared/loop.cpp:192, distributed/loop.cpp:350): seconds;
  * keys total, first_fftw, first_trans, second_fftw, second_trans, plan, plan_flops (+ first_split,
  * first_comm, second_split, second_comm for distributed; extensions h2d, d2h, rows_kernel,
- * cols_kernel, cols_levelA_kernel, cols_levelB_kernel, timer_samples).  Unknown key -> 0.0 like std::map::operator[]. */
+ * cols_kernel, cols_levelA_kernel, cols_levelB_kernel, first_comm_span, second_comm_span, timer_samples).  Unknown key -> 0.0 like std::map::operator[]. */
 double hpxfft_b200_measurement(const hpxfft_b200_plan *, const char *key);
 
 /* Replaces loop::write_plans_to_file (core/src/shared/loop.cpp:194-212): appends a text description
@@ -152,6 +184,9 @@ void hpxfft_b200_host_free(void *ptr);
  *              array, here the transposes are fused away) */
 int hpxfft_b200_r2c_rows(double *host_rows, size_t batch, size_t n_col, int device);
 int hpxfft_b200_c2c_cols(double *host_data, size_t n, size_t width, int device);
+/* variant 0 = the kernels a plan of this length launches (the persistent fused four-step kernel for n > 256),
+ * variant 1 = the unfused launches (single tile / level A + level B) */
+int hpxfft_b200_c2c_cols_variant(double *host_data, size_t n, size_t width, int device, int variant);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(pkg, lib):
 
 
 def test_version_and_constants(pkg, lib):
-    assert lib.hpxfft_b200_version() == 100
+    assert lib.hpxfft_b200_version() == 200
     hdr = open(os.path.join(ROOT, "include", "hpxfft_b200.h")).read()
     assert f"HPXFFT_B200_UNIQUE_ID_BYTES {pkg.capi.UNIQUE_ID_BYTES}" in hdr
     assert f"HPXFFT_B200_IPC_HANDLE_BYTES {pkg.capi.IPC_HANDLE_BYTES}" in hdr

@@ -11,8 +11,12 @@ from conftest import gpu_count
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
-CASES = [(64, 64), (16, 256), (256, 512), (1024, 2048), (2048, 64)]
+CASES = [(64, 64), (16, 256), (256, 512), (1024, 2048), (2048, 64),
+         # long rows with P > 1: C = 2 / C = 4 row kernels (non-FAST addressing, several destination ranks),
+         # long columns with P > 1: the (256,128) fused pair that BASELINE configs 3/4 launch
+         (64, 32768), (32, 65536), (32768, 64), (16, 131072)]
 PIPELINED_CASES = [(1024, 2048), (2048, 512)]   # HPXFFT_B200_CHUNKS=4: sub-slab pipelined exchange
+TRANSPORTS = ["ce", "nccl", "fused"]            # HPXFFT_B200_A2A: transports behind the all_to_all run mode
 
 
 def _free_port():
@@ -38,10 +42,13 @@ def _worker(rank, world, port, q):
             nxl = nx // world
             full = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=11)   # x-dependent input
             ref = oracle.fft_2d_r2c_shared(full, workers=2)
-            for comm in ("all_to_all", "scatter", "p2p"):
+            for comm in ("all_to_all:ce", "all_to_all:nccl", "scatter", "p2p"):
                 slab = full[rank * nxl:(rank + 1) * nxl].copy()
                 fft = pkg.distributed.loop(device=rank)
-                fft.initialize(pkg.vector_2d.from_array(slab), comm, "estimate")
+                if ":" in comm:
+                    os.environ["HPXFFT_B200_A2A"] = comm.split(":")[1]
+                fft.initialize(pkg.vector_2d.from_array(slab), comm.split(":")[0], "estimate")
+                os.environ.pop("HPXFFT_B200_A2A", None)
                 out = fft.fft_2d_r2c().data()
                 err = oracle.rel_l2(out, ref[rank * nxl:(rank + 1) * nxl])
                 # relative to the whole array's norm so that near-empty slabs do not inflate the figure
@@ -51,11 +58,12 @@ def _worker(rank, world, port, q):
                 dist.barrier()
         # opt-in pipelined exchange (row chunks / strip chunks on a second stream)
         os.environ["HPXFFT_B200_CHUNKS"] = "4"
+        os.environ["HPXFFT_B200_A2A"] = "nccl"
         for (nx, ny) in PIPELINED_CASES:
             nxl = nx // world
             full = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=12)
             ref = oracle.fft_2d_r2c_shared(full, workers=2)
-            for comm in ("all_to_all", "scatter"):
+            for comm in ("all_to_all",):
                 fft = pkg.distributed.loop(device=rank)
                 fft.initialize(pkg.vector_2d.from_array(full[rank * nxl:(rank + 1) * nxl].copy()), comm, "estimate")
                 out = fft.fft_2d_r2c().data()
@@ -64,6 +72,24 @@ def _worker(rank, world, port, q):
                 del fft
                 dist.barrier()
         os.environ.pop("HPXFFT_B200_CHUNKS")
+        os.environ.pop("HPXFFT_B200_A2A")
+        # BASELINE configs 3/4 at full size: 32768 x 32768, device-generated separable input, sampled tiles
+        import ctypes as C
+
+        import sampled
+        lib = pkg.capi.load()
+        nx = ny = 32768
+        ref = sampled.SeparableReference(nx, ny, 42)
+        for comm in ("all_to_all:ce", "all_to_all:nccl", "scatter", "p2p"):
+            if ":" in comm:
+                os.environ["HPXFFT_B200_A2A"] = comm.split(":")[1]
+            fft = pkg.distributed.loop(device=rank)
+            fft.initialize(pkg.vector_2d(nx // world, ny + 2, 0.0), comm.split(":")[0], "estimate")
+            os.environ.pop("HPXFFT_B200_A2A", None)
+            r = sampled.check_plan(lib, fft.plan_handle(), nx, ny, rank, world, seed=42, ref=ref)
+            results.append((nx, ny, comm + "+sampled", (r["num"] / r["den"]) ** 0.5, fft.get_measurement("total")))
+            del fft
+            dist.barrier()
         q.put((rank, results))
     except Exception as e:  # pragma: no cover
         import traceback

@@ -61,21 +61,44 @@ def test_r2c_rows(pkg, lib, oracle, ny):
     assert oracle.rel_l2(got, np.ascontiguousarray(ref).view(np.longdouble).reshape(batch, -1)) <= 1e-13
 
 
-@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072])
-def test_c2c_cols(pkg, lib, oracle, n):
+# variant 0 = what a plan launches: the persistent fused four-step kernel for n > 256, i.e. every (N1, N2) pair of
+# launch_fused.cu -- 512 (32,16), 1024 (32,32), 2048 (64,32), 4096 (64,64), 8192 (128,64), 16384 (128,128),
+# 32768 (256,128), 65536 (256,256), 131072 (512,256), 262144 (512,512); variant 1 = the unfused launches.
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144])
+def test_c2c_cols(pkg, lib, oracle, n, variant):
+    if variant == 1 and n <= 256:
+        pytest.skip("single-level lengths have one kernel")
     width = 19 if n <= 16384 else 3          # ragged: one full 16-column tile + a partial one
     rng = np.random.default_rng(n)
     a = rng.uniform(-1, 1, (n, width)) + 1j * rng.uniform(-1, 1, (n, width))
     got = a.copy()
-    pkg.capi.check(lib.hpxfft_b200_c2c_cols(got.ctypes.data, n, width, 0))
+    pkg.capi.check(lib.hpxfft_b200_c2c_cols_variant(got.ctypes.data, n, width, 0, variant))
     import scipy.fft as sfft
     ref = sfft.fft(a.astype(np.clongdouble), axis=0)
     assert oracle.rel_l2(got.view(np.float64), np.ascontiguousarray(ref).view(np.longdouble)) <= 1e-13
 
 
+@pytest.mark.parametrize("n,width", [(512, 16 * 90 + 5), (4096, 16 * 45), (16384, 16 * 50 + 1), (32768, 16 * 24 + 7), (65536, 16 * 12)])
+def test_c2c_cols_fused_ring_wraps(pkg, lib, oracle, n, width):
+    """More strips than scratch-ring slots: the level-A tiles reuse slots that level-B tiles have drained
+    (the dependency counters of cols_fused_kernel), with a ragged last strip."""
+    rng = np.random.default_rng(n + width)
+    a = rng.uniform(-1, 1, (n, width)) + 1j * rng.uniform(-1, 1, (n, width))
+    got = a.copy()
+    pkg.capi.check(lib.hpxfft_b200_c2c_cols_variant(got.ctypes.data, n, width, 0, 0))
+    import scipy.fft as sfft
+    ref = sfft.fft(a, axis=0, workers=8)
+    assert oracle.rel_l2(got.view(np.float64), np.ascontiguousarray(ref).view(np.float64)) <= 1e-13
+
+
 # ---------------------------------------------------------------- 2-D sweeps
 SWEEP = [(2, 2), (2, 4), (4, 2), (8, 8), (16, 64), (64, 16), (1, 32), (32, 2), (128, 128), (256, 512), (512, 256),
-         (1024, 64), (64, 2048), (512, 512), (2048, 1024), (1024, 4096), (64, 32768), (16, 65536), (8, 131072)]
+         (1024, 64), (64, 2048), (512, 512), (2048, 1024), (1024, 4096), (64, 32768), (16, 65536), (8, 131072),
+         # long columns through the 2-D path: every fused pair up to (512,256), short rows
+         (4096, 64), (8192, 64), (16384, 32), (32768, 64), (65536, 32), (131072, 16),
+         # both dimensions long: C=2 rows (ny = 32768) x (256,128) columns, the kernels of BASELINE configs 3/4
+         (32768, 32768 // 64), (512, 32768), (1024, 65536)]
 
 
 @pytest.mark.parametrize("nx,ny", SWEEP)
@@ -194,6 +217,11 @@ def test_write_plans_to_file(pkg, oracle, tmp_path):
     fft.write_plans_to_file(str(path))
     text = path.read_text()
     assert "FFTW r2c 1D plan:" in text and "FFTW c2c 1D plan:" in text
+    assert "single Stockham tile FFT" in text
+    # a two-level size must describe the four-step column plan
+    _, fft2 = shared_fft(pkg, np.zeros((1024, 66)))
+    fft2.write_plans_to_file(str(path))
+    assert "four-step 32 x 32" in path.read_text() and "fused persistent launch" in path.read_text()
 
 
 # ---------------------------------------------------------------- full size (BASELINE config 2)
@@ -233,3 +261,42 @@ def test_c2_16384_separable_and_properties(pkg, lib, oracle):
         assert np.abs(got[1:]).max() <= 1e-12 * np.abs(got[0]).max() * 16384
     finally:
         lib.hpxfft_b200_destroy(plan)
+
+
+# ---------------------------------------------------------------- BASELINE config 3/4 kernels on one GPU
+def test_c3_kernels_32768_sampled(pkg, lib, oracle):
+    """32768 x 32768 on ONE GPU: rows_r2c_kernel<8192,2> and cols_fused_kernel<256,128> -- the kernels the
+    multi-GPU configurations launch -- on device-generated separable input, tile-sampled against the closed form."""
+    import sampled
+    nx = ny = 32768
+    plan = C.c_void_p()
+    pkg.capi.check(lib.hpxfft_b200_create(C.byref(plan), nx, ny + 2, 0, 1, 0, None, b"estimate", None))
+    try:
+        r = sampled.check_plan(lib, plan, nx, ny, 0, 1, seed=42)
+        assert (r["num"] / r["den"]) ** 0.5 <= TOL and r["max_tile_rel"] <= 10 * TOL and r["tiles"] == 16
+    finally:
+        lib.hpxfft_b200_destroy(plan)
+
+
+def test_download_tile_and_device_pointer_upload(pkg, lib, oracle):
+    nx, ny = 64, 256
+    plan, plan2 = C.c_void_p(), C.c_void_p()
+    pkg.capi.check(lib.hpxfft_b200_create(C.byref(plan), nx, ny + 2, 0, 1, 0, None, b"estimate", None))
+    pkg.capi.check(lib.hpxfft_b200_create(C.byref(plan2), nx, ny + 2, 0, 1, 0, None, b"estimate", None))
+    try:
+        a = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=3)
+        pkg.capi.check(lib.hpxfft_b200_upload(plan, a.ctypes.data))
+        t = np.empty((5, 12))
+        pkg.capi.check(lib.hpxfft_b200_download_tile(plan, 7, 5, 20, 12, t.ctypes.data))
+        assert np.array_equal(t, a[7:12, 20:32])
+        assert lib.hpxfft_b200_download_tile(plan, 60, 5, 0, 4, t.ctypes.data) == pkg.capi.EINVAL
+        # device-pointer hand-over (SURVEY 8f N4): plan2 initialised from plan's device slab, result back into it
+        pkg.capi.check(lib.hpxfft_b200_upload(plan2, lib.hpxfft_b200_device_ptr(plan)))
+        pkg.capi.check(lib.hpxfft_b200_execute(plan2))
+        pkg.capi.check(lib.hpxfft_b200_download(plan2, lib.hpxfft_b200_device_ptr(plan)))
+        got = np.empty_like(a)
+        pkg.capi.check(lib.hpxfft_b200_download(plan, got.ctypes.data))
+        assert oracle.rel_l2(got, oracle.fft_2d_r2c_shared(a)) <= TOL
+    finally:
+        lib.hpxfft_b200_destroy(plan)
+        lib.hpxfft_b200_destroy(plan2)
