@@ -42,6 +42,27 @@ def test_cpp_bootstrap_rendezvous(cpp_bins, world, tmp_path):
         assert p.returncode == 0 and "test_bootstrap ok" in o, o
 
 
+def test_cpp_bootstrap_ignores_stale_files(cpp_bins, tmp_path):
+    """A second run in the SAME directory with the SAME MASTER_PORT (and staggered starts) must not pick up the
+    files the first run left behind: the session nonce is drawn afresh and acknowledged by every rank."""
+    import time
+    world = 3
+    for attempt in range(2):
+        procs = []
+        for rank in (2, 1, 0) if attempt else (0, 1, 2):
+            env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_PORT="4713",
+                       HPXFFT_B200_RENDEZVOUS=str(tmp_path))
+            procs.append(subprocess.Popen([os.path.join(cpp_bins, "test_bootstrap")], env=env, stdout=subprocess.PIPE,
+                                          stderr=subprocess.STDOUT, text=True))
+            time.sleep(0.05)
+        for p in procs:
+            o = p.communicate(timeout=120)[0]
+            assert p.returncode == 0 and "test_bootstrap ok" in o, o
+    # data files are removed after the closing barrier; only tiny session / barrier files remain
+    left = [f for f in os.listdir(tmp_path) if "_uid_" in f or "_ipc_" in f]
+    assert all("done" in f for f in left), left
+
+
 @pytest.mark.gpu
 def test_cpp_shared_loop_golden(cpp_bins):
     r = run([os.path.join(cpp_bins, "test_shared_loop")])
