@@ -1,5 +1,7 @@
 // launch_rows.cu -- dispatch of the row (r2c) kernels.
-#include "kernels_rows.cuh"
+#include "kernels_rows_long.cuh"
+
+#include <cstdlib>
 #include "launch_util.h"
 
 namespace hpxfft_b200 {
@@ -35,6 +37,28 @@ template <int M, int C = 1> int launch_rows_big(const hpxfft_b200_plan *p, const
     return launch_rows_big_t<M, C, false>(p, dst, nrows, V, pitch);
 }
 
+// rows longer than one pencil: one persistent CTA per row, C sequential sub-FFTs, L2-resident scratch (kernels_rows_long.cuh)
+template <int C> int launch_rows_long(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+{
+    constexpr size_t smem = rows_long_smem_bytes<C>();
+    if (int rc = ensure_smem(rows_long_kernel<C>, smem, p->device)) return rc;
+    if (!p->zraw) return fail(HPXFFT_B200_ESTATE, "long-row scratch missing");
+    const unsigned cap = (unsigned) (p->sm_count - p->sm_reserve > 0 ? p->sm_count - p->sm_reserve : 1);
+    const unsigned grid = nrows < cap ? nrows : cap;
+    rows_long_kernel<C><<<grid, ROW_THREADS, smem, p->stream>>>(V, pitch, nrows, dst, p->tw_row, p->zraw);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+bool rows_old_path()
+{
+    static const bool v = [] {
+        const char *e = getenv("HPXFFT_B200_ROWS_OLD");
+        return e && e[0] == '1';
+    }();
+    return v;
+}
+
 template <int M> int launch_rows_tiny(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
 {
     const unsigned block = 128, grid = (nrows + block - 1) / block;
@@ -45,7 +69,7 @@ template <int M> int launch_rows_tiny(const hpxfft_b200_plan *p, const RowDst &d
 
 }  // namespace
 
-int rows_launch_count(size_t m) { return m > 16384 ? 2 : 1; }
+int rows_launch_count(size_t m) { return (m > 16384 && rows_old_path()) ? 2 : 1; }
 
 int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m)
 {
@@ -65,9 +89,9 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
     case 2048: return launch_rows_big<2048>(p, dst, nrows, V, pitch);
     case 4096: return launch_rows_big<4096>(p, dst, nrows, V, pitch);
     case 8192: return launch_rows_big<8192>(p, dst, nrows, V, pitch);
-    case 16384: return launch_rows_big<8192, 2>(p, dst, nrows, V, pitch);
-    case 32768: return launch_rows_big<8192, 4>(p, dst, nrows, V, pitch);
-    case 65536: return launch_rows_big<8192, 8>(p, dst, nrows, V, pitch);
+    case 16384: return rows_old_path() ? launch_rows_big<8192, 2>(p, dst, nrows, V, pitch) : launch_rows_long<2>(p, dst, nrows, V, pitch);
+    case 32768: return rows_old_path() ? launch_rows_big<8192, 4>(p, dst, nrows, V, pitch) : launch_rows_long<4>(p, dst, nrows, V, pitch);
+    case 65536: return rows_old_path() ? launch_rows_big<8192, 8>(p, dst, nrows, V, pitch) : launch_rows_long<8>(p, dst, nrows, V, pitch);
     default: return fail(HPXFFT_B200_EINVAL, "unsupported row length ny=%zu (ny/2 must be a power of two <= 65536)", 2 * m);
     }
 }
