@@ -53,6 +53,7 @@ struct hpxfft_b200_plan {
     std::vector<unsigned> ntiles_of, w_of, c0_of;
     // column FFT decomposition
     unsigned n1 = 1, n2 = 1;
+    unsigned col_split = 1;           // radix of the decimation-in-frequency pre-stage folded into the level-A load (nx = col_split*n1*n2)
     bool two_level = false;
     bool rows_generic = false, cols_generic = false; // lengths that are not powers of two
     // device buffers
@@ -103,7 +104,7 @@ int rows_launch_count(size_t m);
 int launch_cols(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles, cd *S, unsigned nx, unsigned n1,
                 unsigned n2, bool two_level, int *launches, cudaEvent_t mid = nullptr);
 int launch_cols_fused(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ct0, unsigned ntiles);
-int fused_blocks_per_sm(unsigned n1, unsigned n2, int *bps);
+int fused_blocks_per_sm(unsigned n1, unsigned n2, unsigned split, int *bps);
 bool fused_pair_exists(unsigned n1, unsigned n2);
 
 int launch_fill(const hpxfft_b200_plan *p, int pattern, unsigned long long seed);

@@ -268,9 +268,11 @@ template <int N1, int N2> __host__ __device__ constexpr size_t fused_tile_bytes(
     return col_tile_bytes(N1) > col_tile_bytes(N2) ? col_tile_bytes(N1) : col_tile_bytes(N2);
 }
 // tile | pass twiddles N1 | pass twiddles N2 (shared with N1's when N1 == N2: same contents) | inter-level row
-template <int N1, int N2> __host__ __device__ constexpr size_t fused_smem_bytes()
+// (+ w_{SPLIT N1}^i, i < N1, for the radix-SPLIT pre-stage)
+template <int N1, int N2, int SPLIT = 1> __host__ __device__ constexpr size_t fused_smem_bytes()
 {
-    return fused_tile_bytes<N1, N2>() + col_tw_bytes(N1) + (N1 == N2 ? 0 : col_tw_bytes(N2)) + N1 * sizeof(cd);
+    return fused_tile_bytes<N1, N2>() + col_tw_bytes(N1) + (N1 == N2 ? 0 : col_tw_bytes(N2)) + N1 * sizeof(cd) +
+           (SPLIT > 1 ? N1 * sizeof(cd) : 0);
 }
 // resident CTAs per SM the register allocator is asked to make room for
 #ifndef HPXFFT_B200_FUSED_MINBLOCKS
@@ -281,24 +283,34 @@ template <int N1, int N2> __host__ __device__ constexpr int fused_min_blocks()
     return fused_threads<N1, N2>() <= 128 ? HPXFFT_B200_FUSED_MINBLOCKS : (fused_threads<N1, N2>() <= 256 ? 2 : 1);
 }
 
-template <int N1, int N2>
+// SPLIT = 2: columns of length nx = 2 n', n' = N1 N2.  One decimation-in-frequency stage over the leading index,
+// y_c2[x'] = w_nx^(x' c2) (Y[x'] + (-1)^c2 Y[x' + n']), is folded into the level-A load, and the two length-n'
+// transforms (spectrum rows kx = c2 + 2 k') run as two adjacent "virtual strips" through the same tiles.  nx = 32768 thus
+// keeps the 128-point tiles (32 KB, 5 CTAs per SM) of the 16384 case instead of 256-point tiles at 2 CTAs per SM;
+// the price is that every input element is loaded twice (the second time from L2).  `ntiles` counts virtual strips.
+template <int N1, int N2, int SPLIT = 1>
 __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, N2>())
     cols_fused_kernel(InterView in, cd *__restrict__ S, ColDst out, const cd *__restrict__ tw, const cd *__restrict__ W2, unsigned ntiles,
                       FusedCtl ctl)
 {
+    static_assert(SPLIT == 1 || SPLIT == 2, "radix of the pre-stage");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NT = fused_threads<N1, N2>();
     cd *smem = reinterpret_cast<cd *>(smem_raw);
     cd *ptw1 = reinterpret_cast<cd *>(smem_raw + fused_tile_bytes<N1, N2>());
     cd *ptw2 = N1 == N2 ? ptw1 : ptw1 + col_tw_entries(N1);
     cd *wil = ptw2 + col_tw_entries(N2);
+    cd *wsp = wil + N1; // SPLIT == 2 only
     __shared__ unsigned s_tile;
     constexpr unsigned PER_GROUP = N1 + N2;
     const unsigned total = (ntiles + ctl.lag) * PER_GROUP;
     const unsigned long long slot_elems = (unsigned long long) N1 * N2 * CW;
 
-    fill_pass_twiddles<N1>(ptw1, tw, (unsigned) N2, (int) threadIdx.x, NT);
-    if (N1 != N2) fill_pass_twiddles<N2>(ptw2, tw, (unsigned) N1, (int) threadIdx.x, NT);
+    fill_pass_twiddles<N1>(ptw1, tw, (unsigned) (SPLIT * N2), (int) threadIdx.x, NT);
+    if (N1 != N2) fill_pass_twiddles<N2>(ptw2, tw, (unsigned) (SPLIT * N1), (int) threadIdx.x, NT);
+    if constexpr (SPLIT > 1) {
+        for (int i = threadIdx.x; i < N1; i += NT) wsp[i] = ldtw(tw, (unsigned) i * (unsigned) N2); // w_nx^(i N2) = w_{SPLIT N1}^i
+    }
 
     // dependency of tile t: (counter address, target) -- nullptr when there is none
     auto dep_of = [&](unsigned t, unsigned &target) -> const unsigned * {
@@ -350,30 +362,43 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
             // level A: tile x2 = r of strip g
             if (g < ntiles) {
 #ifdef HPXFFT_B200_DIAG_WRAP
-                const unsigned x2 = r, ct = (ctl.ct0 + g) & 1u;
+                const unsigned x2 = r, ct = (ctl.ct0 + g / SPLIT) & 1u;
 #else
-                const unsigned x2 = r, ct = ctl.ct0 + g;
+                const unsigned x2 = r, ct = ctl.ct0 + g / SPLIT;
 #endif
                 for (int i = threadIdx.x; i < N1; i += NT) wil[i] = ldtw(W2, x2 * (unsigned) N1 + (unsigned) i);
                 cd *Sct = S + (unsigned long long) (g % ctl.nslot) * slot_elems;
-                auto ld = [&](int i, int c) -> cd { return ld_stream(inter_ptr(in, (unsigned) i * N2 + x2, ct, (unsigned) c)); };
                 auto st = [&](int k1, int c, cd val) { st_cg(Sct + ((unsigned long long) k1 * N2 + x2) * CW + c, cmul(val, wil[k1])); };
-                tile_fft<N1>(smem, ptw1, ld, st);
+                if constexpr (SPLIT == 1) {
+                    auto ld = [&](int i, int c) -> cd { return ld_stream(inter_ptr(in, (unsigned) i * N2 + x2, ct, (unsigned) c)); };
+                    tile_fft<N1>(smem, ptw1, ld, st);
+                } else {
+                    const unsigned c2 = g % SPLIT;
+                    const cd ws = ldtw(tw, x2); // w_nx^x2
+                    // both halves of the column are read with default caching: the sibling virtual strip re-reads them from L2
+                    auto ld = [&](int i, int c) -> cd {
+                        const unsigned x = (unsigned) i * N2 + x2;
+                        const cd a = ld_cg(inter_ptr(in, x, ct, (unsigned) c)), b = ld_cg(inter_ptr(in, x + (unsigned) (N1 * N2), ct, (unsigned) c));
+                        return c2 ? cmul(csub(a, b), cmul(ws, wsp[i])) : cadd(a, b);
+                    };
+                    tile_fft<N1>(smem, ptw1, ld, st);
+                }
                 done = ctl.doneA + g;
                 synced = col_npass(N1) >= 2;
             }
         } else if (g >= ctl.lag) {
             // level B: tile k1 = r - N2 of strip g - lag
 #ifdef HPXFFT_B200_DIAG_WRAP
-            const unsigned k1 = r - N2, sl = g - ctl.lag, ct = (ctl.ct0 + sl) & 1u;
+            const unsigned k1 = r - N2, sl = g - ctl.lag, ct = (ctl.ct0 + sl / SPLIT) & 1u;
 #else
-            const unsigned k1 = r - N2, sl = g - ctl.lag, ct = ctl.ct0 + sl;
+            const unsigned k1 = r - N2, sl = g - ctl.lag, ct = ctl.ct0 + sl / SPLIT;
 #endif
+            const unsigned c2 = sl % SPLIT;
             const cd *Sk = S + (unsigned long long) (sl % ctl.nslot) * slot_elems + (unsigned long long) k1 * N2 * CW;
             auto ld = [&](int i, int c) -> cd { return ld_cg(Sk + (unsigned) i * CW + c); };
             auto st = [&](int k2, int c, cd val) {
                 const unsigned kl = ct * CW + c;
-                if (kl < out.w) st_stream(coldst_ptr(out, k1 + (unsigned) N1 * (unsigned) k2, kl), val);
+                if (kl < out.w) st_stream(coldst_ptr(out, c2 + (unsigned) SPLIT * (k1 + (unsigned) N1 * (unsigned) k2), kl), val);
             };
             tile_fft<N2>(smem, ptw2, ld, st);
             synced = col_npass(N2) >= 2;
@@ -397,7 +422,9 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
         }
         __syncthreads();
         if (threadIdx.x == 0 && done) {
+#ifndef HPXFFT_B200_DIAG_NOFENCE
             __threadfence();
+#endif
             atomicAdd(done, 1u);
         }
         if (!s_ready) {

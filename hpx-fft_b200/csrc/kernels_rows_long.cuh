@@ -118,22 +118,49 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
                 q = q == MM ? 0u : q;
                 return ld_cg(zs + (size_t) (q % C) * M + q / C);
             };
-            for (unsigned blk = warp; blk < MM / 64; blk += ROW_THREADS / 32) {
-                const unsigned k0 = blk * 32u, k = k0 + lane, mk = MM - k;
-                cd xk, xmk;
-                herm_pair(zat(k), zat(mk), ldtw(tw, k), xk, xmk);
-                st_stream(rowdst_ptr(dst, row, k), xk);
-                // mirrored bins: lanes 1..31 hold m-k0-1 ... m-k0-31; lane 0 completes the aligned block with
-                // bin m-k0-32 (the mirror of k0+32) instead of its own m-k0, which the previous block stored
-                unsigned mb = mk;
-                if (lane == 0) {
-                    if (k0 == 0) st_stream(rowdst_ptr(dst, row, MM), xmk); // Nyquist bin: the lone last column
-                    const unsigned k2 = k0 + 32u;
-                    cd x2;
-                    herm_pair(zat(k2), zat(MM - k2), ldtw(tw, k2), x2, xmk);
-                    mb = MM - k2;
+            // UB blocks per batch: all loads of a batch are issued before the first Hermitian split, so that the loop
+            // pays the L2 latency once per batch instead of once per block
+            constexpr int UB = 8;
+            static_assert((MM / 64) % (UB * (ROW_THREADS / 32)) == 0, "blocks per warp must be a multiple of the batch");
+            for (unsigned blk0 = warp * UB; blk0 < MM / 64; blk0 += UB * (ROW_THREADS / 32)) {
+                cd za[UB], zb[UB], wk[UB], ya, yb, wy;
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const unsigned k = (blk0 + u) * 32u + lane;
+                    za[u] = zat(k);
+                    zb[u] = zat(MM - k);
+                    wk[u] = ldtw(tw, k);
                 }
-                st_stream(rowdst_ptr(dst, row, mb), xmk);
+                // lane 0 completes every mirrored block with bin m-k0-32, the mirror of k0+32; lanes u < UB fetch those
+                // operands (one block each) and hand them to lane 0 through shuffles below
+                if (lane < UB) {
+                    const unsigned k2 = (blk0 + lane) * 32u + 32u;
+                    ya = zat(k2);
+                    yb = zat(MM - k2);
+                    wy = ldtw(tw, k2);
+                } else {
+                    ya = yb = wy = make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const unsigned k0 = (blk0 + u) * 32u, k = k0 + lane;
+                    cd xk, xmk;
+                    herm_pair(za[u], zb[u], wk[u], xk, xmk);
+                    st_stream(rowdst_ptr(dst, row, k), xk);
+                    // operands of the extra bin, broadcast from lane u
+                    cd ea, eb, ew;
+                    ea.x = __shfl_sync(0xffffffffu, ya.x, u); ea.y = __shfl_sync(0xffffffffu, ya.y, u);
+                    eb.x = __shfl_sync(0xffffffffu, yb.x, u); eb.y = __shfl_sync(0xffffffffu, yb.y, u);
+                    ew.x = __shfl_sync(0xffffffffu, wy.x, u); ew.y = __shfl_sync(0xffffffffu, wy.y, u);
+                    unsigned mb = MM - k;
+                    if (lane == 0) {
+                        if (k0 == 0) st_stream(rowdst_ptr(dst, row, MM), xmk); // Nyquist bin: the lone last column
+                        cd x2;
+                        herm_pair(ea, eb, ew, x2, xmk);
+                        mb = MM - (k0 + 32u);
+                    }
+                    st_stream(rowdst_ptr(dst, row, mb), xmk);
+                }
             }
         }
         __syncthreads(); // assembly reads are done before the next row overwrites the scratch

@@ -27,19 +27,21 @@ namespace hpxfft_b200 {
 
 namespace {
 
-template <int N1, int N2> int fused_occupancy(int *blocks_per_sm)
+template <int N1, int N2, int SPLIT> int fused_occupancy(int *blocks_per_sm)
 {
-    constexpr size_t smem = fused_smem_bytes<N1, N2>();
-    if (int rc = set_smem(cols_fused_kernel<N1, N2>, smem)) return rc;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cols_fused_kernel<N1, N2>, fused_threads<N1, N2>(), smem));
+    constexpr size_t smem = fused_smem_bytes<N1, N2, SPLIT>();
+    if (int rc = set_smem(cols_fused_kernel<N1, N2, SPLIT>, smem)) return rc;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cols_fused_kernel<N1, N2, SPLIT>, fused_threads<N1, N2>(), smem));
     return 0;
 }
 
-template <int N1, int N2>
-int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ct0, unsigned ntiles)
+// ct0 / nstrips in real strips; the kernel sees SPLIT virtual strips per real one
+template <int N1, int N2, int SPLIT>
+int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ct0, unsigned nstrips)
 {
-    constexpr size_t smem = fused_smem_bytes<N1, N2>();
-    if (int rc = ensure_smem(cols_fused_kernel<N1, N2>, smem, p->device)) return rc;
+    constexpr size_t smem = fused_smem_bytes<N1, N2, SPLIT>();
+    if (int rc = ensure_smem(cols_fused_kernel<N1, N2, SPLIT>, smem, p->device)) return rc;
+    const unsigned ntiles = nstrips * SPLIT;
     CU(cudaMemsetAsync(p->ctl, 0, (1 + 2 * (size_t) ntiles) * sizeof(unsigned), p->stream));
     FusedCtl ctl;
     ctl.counter = p->ctl;
@@ -56,7 +58,7 @@ int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const Co
         }();
         ctl.discard = (unsigned) discard;
     }
-    cols_fused_kernel<N1, N2><<<p->fused_grid, fused_threads<N1, N2>(), smem, p->stream>>>(in, p->S, out, p->tw_col, p->tw_il, ntiles, ctl);
+    cols_fused_kernel<N1, N2, SPLIT><<<p->fused_grid, fused_threads<N1, N2>(), smem, p->stream>>>(in, p->S, out, p->tw_col, p->tw_il, ntiles, ctl);
     CU(cudaGetLastError());
     return 0;
 }
@@ -66,17 +68,23 @@ int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const Co
 // returns 1 when the pair does not belong to this group
 int GROUP_FN(launch_cols_fused)(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ct0, unsigned ntiles, int *rc)
 {
-#define X(A, B) if (p->n1 == A && p->n2 == B) { *rc = launch_cols_fused_t<A, B>(p, in, out, ct0, ntiles); return 0; }
+#define X(A, B) if (p->n1 == A && p->n2 == B && p->col_split == 1) { *rc = launch_cols_fused_t<A, B, 1>(p, in, out, ct0, ntiles); return 0; }
     FUSED_PAIRS(X)
 #undef X
+#if HPXFFT_B200_FUSED_GROUP == 1
+    if (p->n1 == 128 && p->n2 == 128 && p->col_split == 2) { *rc = launch_cols_fused_t<128, 128, 2>(p, in, out, ct0, ntiles); return 0; }
+#endif
     return 1;
 }
 
-int GROUP_FN(fused_blocks_per_sm)(unsigned n1, unsigned n2, int *bps, int *rc)
+int GROUP_FN(fused_blocks_per_sm)(unsigned n1, unsigned n2, unsigned split, int *bps, int *rc)
 {
-#define X(A, B) if (n1 == A && n2 == B) { *rc = fused_occupancy<A, B>(bps); return 0; }
+#define X(A, B) if (n1 == A && n2 == B && split == 1) { *rc = fused_occupancy<A, B, 1>(bps); return 0; }
     FUSED_PAIRS(X)
 #undef X
+#if HPXFFT_B200_FUSED_GROUP == 1
+    if (n1 == 128 && n2 == 128 && split == 2) { *rc = fused_occupancy<128, 128, 2>(bps); return 0; }
+#endif
     return 1;
 }
 

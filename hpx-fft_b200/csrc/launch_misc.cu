@@ -7,7 +7,7 @@ namespace hpxfft_b200 {
 
 #define DECL_GROUP(g)                                                                                                          \
     int launch_cols_fused_g##g(const hpxfft_b200_plan *, const InterView &, const ColDst &, unsigned, unsigned, int *);        \
-    int fused_blocks_per_sm_g##g(unsigned, unsigned, int *, int *);
+    int fused_blocks_per_sm_g##g(unsigned, unsigned, unsigned, int *, int *);
 DECL_GROUP(0) DECL_GROUP(1) DECL_GROUP(2) DECL_GROUP(3)
 #undef DECL_GROUP
 
@@ -22,13 +22,13 @@ int launch_cols_fused(const hpxfft_b200_plan *p, const InterView &in, const ColD
     return fail(HPXFFT_B200_EINVAL, "no fused column kernel for %u x %u", p->n1, p->n2);
 }
 
-int fused_blocks_per_sm(unsigned n1, unsigned n2, int *bps)
+int fused_blocks_per_sm(unsigned n1, unsigned n2, unsigned split, int *bps)
 {
     int rc = 0;
-    if (!fused_blocks_per_sm_g0(n1, n2, bps, &rc)) return rc;
-    if (!fused_blocks_per_sm_g1(n1, n2, bps, &rc)) return rc;
-    if (!fused_blocks_per_sm_g2(n1, n2, bps, &rc)) return rc;
-    if (!fused_blocks_per_sm_g3(n1, n2, bps, &rc)) return rc;
+    if (!fused_blocks_per_sm_g0(n1, n2, split, bps, &rc)) return rc;
+    if (!fused_blocks_per_sm_g1(n1, n2, split, bps, &rc)) return rc;
+    if (!fused_blocks_per_sm_g2(n1, n2, split, bps, &rc)) return rc;
+    if (!fused_blocks_per_sm_g3(n1, n2, split, bps, &rc)) return rc;
     return fail(HPXFFT_B200_EINVAL, "no fused column kernel for %u x %u", n1, n2);
 }
 

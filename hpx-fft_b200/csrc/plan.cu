@@ -98,8 +98,20 @@ void make_interlevel(std::vector<double2> &w2, const std::vector<double2> &t, un
         for (size_t k1 = 0; k1 < n1; ++k1) w2[x2 * n1 + k1] = t[(k1 * x2) % nx];
 }
 
-void choose_col_split(size_t nx, unsigned &n1, unsigned &n2, bool &two_level)
+// nx = split * n1 * n2.  split = 2 only for nx = 32768: the 128 x 128 tiles of the 16384 case run at 5 CTAs per SM,
+// the 256 x 128 decomposition at 2 (HPXFFT_B200_COLSPLIT=0 restores it for A/B runs).
+void choose_col_split(size_t nx, unsigned &n1, unsigned &n2, bool &two_level, unsigned *split = nullptr)
 {
+    if (split) {
+        *split = 1;
+        const char *e = getenv("HPXFFT_B200_COLSPLIT");
+        if (nx == 32768 && !(e && e[0] == '0')) {
+            *split = 2;
+            n1 = n2 = 128;
+            two_level = true;
+            return;
+        }
+    }
     if (nx <= 256) {
         two_level = false;
         n1 = (unsigned) nx;
@@ -839,7 +851,7 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     p->w = p->w_of[rank];
     p->c0 = p->c0_of[rank];
     p->ntiles = p->ntiles_of[rank];
-    choose_col_split(p->nx, p->n1, p->n2, p->two_level);
+    choose_col_split(p->nx, p->n1, p->n2, p->two_level, &p->col_split);
     if (p->cols_generic) {
         p->two_level = false;
         p->n1 = (unsigned) p->nx;
@@ -864,6 +876,10 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     if (p->two_level) {
         const char *e = getenv("HPXFFT_B200_FUSED");
         p->fused = !(e && e[0] == '0') && fused_pair_exists(p->n1, p->n2);
+        if (!p->fused && p->col_split > 1) { // the pre-stage only exists in the fused kernel
+            p->col_split = 1;
+            choose_col_split(p->nx, p->n1, p->n2, p->two_level);
+        }
     }
     const bool nccl_pipelined = p->transport == TR_NCCL && mode == MODE_ALL_TO_ALL && env_int("HPXFFT_B200_CHUNKS", 1) > 1;
     if (nccl_pipelined) {
@@ -881,7 +897,7 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     } while (0)
     if (p->fused) {
         int bps = 1;
-        if (int rc = fused_blocks_per_sm(p->n1, p->n2, &bps)) return bail(rc);
+        if (int rc = fused_blocks_per_sm(p->n1, p->n2, p->col_split, &bps)) return bail(rc);
         {
             const int v = env_int("HPXFFT_B200_FUSED_BPS", 0);
             if (v >= 1 && v < bps) bps = v;
@@ -898,8 +914,8 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
             const int v = env_int("HPXFFT_B200_NSLOT", 0);
             if (v > (int) p->lag) p->nslot = (unsigned) v;
         }
-        if (p->nslot > p->ntiles) p->nslot = p->ntiles > 0 ? p->ntiles : 1;
-        p->bytesS = (size_t) p->nslot * p->nx * CW * sizeof(cd);
+        if (p->nslot > p->ntiles * p->col_split) p->nslot = p->ntiles > 0 ? p->ntiles * p->col_split : 1;
+        p->bytesS = (size_t) p->nslot * (p->nx / p->col_split) * CW * sizeof(cd);
     }
     if (p->transport == TR_NCCL || p->transport == TR_CE) {
         size_t tiles_all = 0;
@@ -918,7 +934,7 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         CUB(cudaMalloc(&p->zraw, rows * p->m * sizeof(cd)));
     }
     if (p->bytesS) CUB(cudaMalloc(&p->S, p->bytesS));
-    if (p->fused) CUB(cudaMalloc(&p->ctl, (1 + 2 * (size_t) p->ntiles) * sizeof(unsigned)));
+    if (p->fused) CUB(cudaMalloc(&p->ctl, (1 + 2 * (size_t) p->ntiles * p->col_split) * sizeof(unsigned)));
     if (p->bytesA) CUB(cudaMalloc(&p->bufA, p->bytesA));
     CUB(cudaMemsetAsync(p->V, 0, bytesV, p->stream));
     CUB(cudaMemsetAsync(p->bufB, 0, p->bytesB, p->stream));
@@ -936,6 +952,7 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         CUB(cudaStreamSynchronize(p->stream));
         if (p->two_level) {
             std::vector<double2> w2;
+            if (p->col_split > 1) make_twiddles(t, p->nx / p->col_split); // inter-level factors of the length-n' transforms
             make_interlevel(w2, t, p->n1, p->n2);
             CUB(cudaMalloc(&p->tw_il, w2.size() * sizeof(double2)));
             CUB(cudaMemcpyAsync(p->tw_il, w2.data(), w2.size() * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
@@ -1009,8 +1026,9 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     if (p->cols_generic)
         snprintf(buf, sizeof(buf), "c2c columns: n=%zu direct DFT (length is not a power of two)", p->nx);
     else if (p->two_level)
-        snprintf(buf, sizeof(buf), "c2c columns: n=%zu four-step %u x %u on %d-column tiles (level A strided + twiddle, level B contiguous)%s",
-                 p->nx, p->n1, p->n2, CW, p->fused ? ", fused persistent launch with L2-resident scratch ring" : "");
+        snprintf(buf, sizeof(buf), "c2c columns: n=%zu %sfour-step %u x %u on %d-column tiles (level A strided + twiddle, level B contiguous)%s",
+                 p->nx, p->col_split > 1 ? "radix-2 DIF pre-stage + " : "", p->n1, p->n2, CW,
+                 p->fused ? ", fused persistent launch with L2-resident scratch ring" : "");
     else
         snprintf(buf, sizeof(buf), "c2c columns: n=%zu single Stockham tile FFT on %d-column tiles", p->nx, CW);
     p->col_desc = buf;
@@ -1360,7 +1378,7 @@ int hpxfft_b200_c2c_cols_variant(double *host_data, size_t n, size_t width, int 
     p->cy = width;
     p->w = (unsigned) width;
     p->ntiles = (unsigned) ((width + CW - 1) / CW);
-    choose_col_split(n, p->n1, p->n2, p->two_level);
+    choose_col_split(n, p->n1, p->n2, p->two_level, variant == 0 ? &p->col_split : nullptr);
     p->fused = variant == 0 && p->two_level && fused_pair_exists(p->n1, p->n2);
     const size_t bytes = n * width * sizeof(cd), tbytes = (size_t) p->ntiles * n * CW * sizeof(cd);
     cd *A = nullptr;
@@ -1392,7 +1410,7 @@ int hpxfft_b200_c2c_cols_variant(double *host_data, size_t n, size_t width, int 
     size_t sbytes = tbytes;
     if (p->fused) {
         int bps = 1;
-        if ((rc = fused_blocks_per_sm(p->n1, p->n2, &bps))) {
+        if ((rc = fused_blocks_per_sm(p->n1, p->n2, p->col_split, &bps))) {
             cleanup();
             return rc;
         }
@@ -1400,15 +1418,16 @@ int hpxfft_b200_c2c_cols_variant(double *host_data, size_t n, size_t width, int 
         const unsigned per_group = p->n1 + p->n2;
         p->lag = (unsigned) ((3 * (size_t) p->fused_grid / 2 + per_group - 1) / per_group) + 1;
         p->nslot = 2 * p->lag + 1;
-        if (p->nslot > p->ntiles) p->nslot = p->ntiles;
-        sbytes = (size_t) p->nslot * n * CW * sizeof(cd);
-        CUC(cudaMalloc(&p->ctl, (1 + 2 * (size_t) p->ntiles) * sizeof(unsigned)));
+        if (p->nslot > p->ntiles * p->col_split) p->nslot = p->ntiles * p->col_split;
+        sbytes = (size_t) p->nslot * (n / p->col_split) * CW * sizeof(cd);
+        CUC(cudaMalloc(&p->ctl, (1 + 2 * (size_t) p->ntiles * p->col_split) * sizeof(unsigned)));
     }
     if (p->two_level) CUC(cudaMalloc(&p->S, sbytes));
     CUC(cudaMalloc(&p->tw_col, t.size() * sizeof(double2)));
     CUC(cudaMemcpyAsync(p->tw_col, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
     std::vector<double2> w2;
     if (p->two_level) {
+        if (p->col_split > 1) make_twiddles(t, n / p->col_split);
         make_interlevel(w2, t, p->n1, p->n2);
         CUC(cudaMalloc(&p->tw_il, w2.size() * sizeof(double2)));
         CUC(cudaMemcpyAsync(p->tw_il, w2.data(), w2.size() * sizeof(double2), cudaMemcpyHostToDevice, p->stream));

@@ -79,6 +79,19 @@ def test_c2c_cols(pkg, lib, oracle, n, variant):
     assert oracle.rel_l2(got.view(np.float64), np.ascontiguousarray(ref).view(np.longdouble)) <= 1e-13
 
 
+def test_c2c_cols_32768_without_prestage(pkg, lib, oracle, monkeypatch):
+    """nx = 32768 runs as radix-2 pre-stage + 128 x 128 by default; HPXFFT_B200_COLSPLIT=0 selects the 256 x 128 pair."""
+    monkeypatch.setenv("HPXFFT_B200_COLSPLIT", "0")
+    n, width = 32768, 16 * 9 + 3
+    rng = np.random.default_rng(5)
+    a = rng.uniform(-1, 1, (n, width)) + 1j * rng.uniform(-1, 1, (n, width))
+    got = a.copy()
+    pkg.capi.check(lib.hpxfft_b200_c2c_cols_variant(got.ctypes.data, n, width, 0, 0))
+    import scipy.fft as sfft
+    ref = sfft.fft(a, axis=0, workers=8)
+    assert oracle.rel_l2(got.view(np.float64), np.ascontiguousarray(ref).view(np.float64)) <= 1e-13
+
+
 @pytest.mark.parametrize("n,width", [(512, 16 * 90 + 5), (4096, 16 * 45), (16384, 16 * 50 + 1), (32768, 16 * 24 + 7), (65536, 16 * 12)])
 def test_c2c_cols_fused_ring_wraps(pkg, lib, oracle, n, width):
     """More strips than scratch-ring slots: the level-A tiles reuse slots that level-B tiles have drained
