@@ -141,4 +141,30 @@ __device__ __forceinline__ void st_cg(cd *p, cd v)
     asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
+// L2 eviction-priority hints (createpolicy).  evict_last: data that is re-read soon by the same kernel (per-CTA scratch,
+// a row that the next sub-FFT reads again) must survive the flood of streaming traffic that passes through L2 in the
+// meantime; evict_first on the last use hands the lines back.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ cd ld_cg_hint(const cd *p, unsigned long long policy)
+{
+    cd r;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ void st_cg_hint(cd *p, cd v, unsigned long long policy)
+{
+    asm volatile("st.global.cg.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
+}
+
 }  // namespace hpxfft_b200

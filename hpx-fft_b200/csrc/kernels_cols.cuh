@@ -370,7 +370,11 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
                 cd *Sct = S + (unsigned long long) (g % ctl.nslot) * slot_elems;
                 auto st = [&](int k1, int c, cd val) { st_cg(Sct + ((unsigned long long) k1 * N2 + x2) * CW + c, cmul(val, wil[k1])); };
                 if constexpr (SPLIT == 1) {
+#ifdef HPXFFT_B200_DIAG_NOLOAD_I
+                    auto ld = [&](int i, int c) -> cd { return make_double2((double) (i + x2), (double) c); };
+#else
                     auto ld = [&](int i, int c) -> cd { return ld_stream(inter_ptr(in, (unsigned) i * N2 + x2, ct, (unsigned) c)); };
+#endif
                     tile_fft<N1>(smem, ptw1, ld, st);
                 } else {
                     const unsigned c2 = g % SPLIT;
@@ -398,7 +402,11 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
             auto ld = [&](int i, int c) -> cd { return ld_cg(Sk + (unsigned) i * CW + c); };
             auto st = [&](int k2, int c, cd val) {
                 const unsigned kl = ct * CW + c;
+#ifdef HPXFFT_B200_DIAG_NOSTORE_V
+                if (kl < out.w && val.x == 1.2345678e300) st_stream(coldst_ptr(out, c2 + (unsigned) SPLIT * (k1 + (unsigned) N1 * (unsigned) k2), kl), val);
+#else
                 if (kl < out.w) st_stream(coldst_ptr(out, c2 + (unsigned) SPLIT * (k1 + (unsigned) N1 * (unsigned) k2), kl), val);
+#endif
             };
             tile_fft<N2>(smem, ptw2, ld, st);
             synced = col_npass(N2) >= 2;

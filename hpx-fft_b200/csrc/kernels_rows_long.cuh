@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
     cd *tw2 = tw1 + 512;
     cd *twc = tw2 + 16 * 256;
     cd *zs = scratch + (size_t) blockIdx.x * MM; // [c][k2], rewritten for every row: stays in L2
+    const unsigned long long keep = l2_policy_evict_last(), drop = l2_policy_evict_first();
 
     // tables (tw = w_n^i, n = 2 m):  w_512^(r k) = w_n^(r k n/512),  w_M^(r j) = w_n^(2 C r j),  w_{32C}^i = w_n^(512 i)
     for (int i = lt; i < 512; i += ROW_THREADS) {
@@ -62,18 +63,19 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
             // ---- pass 0: DIF combine over the C blocks of the row, twiddle, radix 32 ----
             // y_c[idx], idx = lt + 256 r:  w_m^(idx c) = w_m^(lt c) * w_{32C}^(r c)
             const cd wbase = c ? ldtw(tw, 2u * (unsigned) lt * (unsigned) c) : make_double2(1.0, 0.0);
+            const unsigned long long rowpol = c == C - 1 ? drop : keep; // the row is read C times: keep it in L2 until the last one
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
                 const cd *p = zrow + lt + r * 256;
                 cd acc;
                 if constexpr (C == 2) {
-                    const cd a = ld_cg(p), b = ld_cg(p + M);
+                    const cd a = ld_cg_hint(p, rowpol), b = ld_cg_hint(p + M, rowpol);
                     acc = c ? csub(a, b) : cadd(a, b);
                 } else {
-                    acc = ld_cg(p);
+                    acc = ld_cg_hint(p, rowpol);
 #pragma unroll
                     for (int j1 = 1; j1 < C; ++j1) {
-                        const cd z = ld_cg(p + j1 * M);
+                        const cd z = ld_cg_hint(p + j1 * M, rowpol);
                         acc = c ? cadd(acc, cmul(z, twc[(32 * j1 * c) & (32 * C - 1)])) : cadd(acc, z);
                     }
                 }
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
                 fft_dif<16>(w);
                 cd *zc = zs + (size_t) c * M + j;
 #pragma unroll
-                for (int s = 0; s < 16; ++s) st_cg(zc + s * 512, w[bitrev(s, 4)]);
+                for (int s = 0; s < 16; ++s) st_cg_hint(zc + s * 512, w[bitrev(s, 4)], keep);
             }
         }
         __syncthreads(); // the whole raw spectrum is in the scratch (global writes are visible block-wide after the barrier)
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
             const unsigned warp = (unsigned) lt >> 5, lane = (unsigned) lt & 31u;
             auto zat = [&](unsigned q) -> cd {
                 q = q == MM ? 0u : q;
-                return ld_cg(zs + (size_t) (q % C) * M + q / C);
+                return ld_cg_hint(zs + (size_t) (q % C) * M + q / C, keep);
             };
             // UB blocks per batch: all loads of a batch are issued before the first Hermitian split, so that the loop
             // pays the L2 latency once per batch instead of once per block

@@ -1,5 +1,6 @@
 // launch_rows.cu -- dispatch of the row (r2c) kernels.
 #include "kernels_rows_long.cuh"
+#include "kernels_rows_v2.cuh"
 
 #include <cstdlib>
 #include "launch_util.h"
@@ -50,6 +51,26 @@ template <int C> int launch_rows_long(const hpxfft_b200_plan *p, const RowDst &d
     return 0;
 }
 
+// ny = 16384: warp-local in-place sub-FFTs (kernels_rows_v2.cuh); HPXFFT_B200_ROWS_V1=1 selects the Stockham kernel (A/B runs)
+template <bool FAST> int launch_rows_v2_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+{
+    if (int rc = ensure_smem(rows_r2c_v2_kernel<FAST>, rv2::SMEM, p->device)) return rc;
+    const unsigned cap = (unsigned) (p->sm_count - p->sm_reserve > 0 ? p->sm_count - p->sm_reserve : 1);
+    const unsigned grid = nrows < cap ? nrows : cap;
+    rows_r2c_v2_kernel<FAST><<<grid, ROW_THREADS, rv2::SMEM, p->stream>>>(V, pitch, nrows, dst, p->tw_row);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+bool rows_v1_path()
+{
+    static const bool v = [] {
+        const char *e = getenv("HPXFFT_B200_ROWS_V1");
+        return e && e[0] == '1';
+    }();
+    return v;
+}
+
 bool rows_old_path()
 {
     static const bool v = [] {
@@ -88,7 +109,9 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
     case 1024: return launch_rows_big<1024>(p, dst, nrows, V, pitch);
     case 2048: return launch_rows_big<2048>(p, dst, nrows, V, pitch);
     case 4096: return launch_rows_big<4096>(p, dst, nrows, V, pitch);
-    case 8192: return launch_rows_big<8192>(p, dst, nrows, V, pitch);
+    case 8192:
+        if (rows_v1_path()) return launch_rows_big<8192>(p, dst, nrows, V, pitch);
+        return dst.P == 1 ? launch_rows_v2_t<true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false>(p, dst, nrows, V, pitch);
     case 16384: return rows_old_path() ? launch_rows_big<8192, 2>(p, dst, nrows, V, pitch) : launch_rows_long<2>(p, dst, nrows, V, pitch);
     case 32768: return rows_old_path() ? launch_rows_big<8192, 4>(p, dst, nrows, V, pitch) : launch_rows_long<4>(p, dst, nrows, V, pitch);
     case 65536: return rows_old_path() ? launch_rows_big<8192, 8>(p, dst, nrows, V, pitch) : launch_rows_long<8>(p, dst, nrows, V, pitch);

@@ -98,14 +98,15 @@ void make_interlevel(std::vector<double2> &w2, const std::vector<double2> &t, un
         for (size_t k1 = 0; k1 < n1; ++k1) w2[x2 * n1 + k1] = t[(k1 * x2) % nx];
 }
 
-// nx = split * n1 * n2.  split = 2 only for nx = 32768: the 128 x 128 tiles of the 16384 case run at 5 CTAs per SM,
-// the 256 x 128 decomposition at 2 (HPXFFT_B200_COLSPLIT=0 restores it for A/B runs).
+// nx = split * n1 * n2.  split = 2 (opt-in, HPXFFT_B200_COLSPLIT=1, nx = 32768 only) runs the 128 x 128 tiles of the 16384 case
+// (5 CTAs per SM) behind a radix-2 pre-stage instead of 256 x 128 tiles (2 CTAs per SM).  Measured SLOWER (7.9 vs 6.5 ms per
+// 32768^2: every input element is loaded twice and the second load is not served by L2), so it is not the default.
 void choose_col_split(size_t nx, unsigned &n1, unsigned &n2, bool &two_level, unsigned *split = nullptr)
 {
     if (split) {
         *split = 1;
         const char *e = getenv("HPXFFT_B200_COLSPLIT");
-        if (nx == 32768 && !(e && e[0] == '0')) {
+        if (nx == 32768 && e && e[0] == '1') {
             *split = 2;
             n1 = n2 = 128;
             two_level = true;

@@ -14,7 +14,8 @@ TOL = 1e-12
 CASES = [(64, 64), (16, 256), (256, 512), (1024, 2048), (2048, 64),
          # long rows with P > 1: C = 2 / C = 4 row kernels (non-FAST addressing, several destination ranks),
          # long columns with P > 1: the (256,128) fused pair that BASELINE configs 3/4 launch
-         (64, 32768), (32, 65536), (32768, 64), (16, 131072)]
+         (64, 32768), (32, 65536), (32768, 64), (16, 131072),
+         (296, 16384)]   # ny = 16384 with P > 1: rows_r2c_v2_kernel<false>, two full waves of persistent CTAs
 PIPELINED_CASES = [(1024, 2048), (2048, 512)]   # HPXFFT_B200_CHUNKS=4: sub-slab pipelined exchange
 TRANSPORTS = ["ce", "nccl", "fused"]            # HPXFFT_B200_A2A: transports behind the all_to_all run mode
 

@@ -79,9 +79,9 @@ def test_c2c_cols(pkg, lib, oracle, n, variant):
     assert oracle.rel_l2(got.view(np.float64), np.ascontiguousarray(ref).view(np.longdouble)) <= 1e-13
 
 
-def test_c2c_cols_32768_without_prestage(pkg, lib, oracle, monkeypatch):
-    """nx = 32768 runs as radix-2 pre-stage + 128 x 128 by default; HPXFFT_B200_COLSPLIT=0 selects the 256 x 128 pair."""
-    monkeypatch.setenv("HPXFFT_B200_COLSPLIT", "0")
+def test_c2c_cols_32768_with_prestage(pkg, lib, oracle, monkeypatch):
+    """nx = 32768 runs on 256 x 128 tiles by default; HPXFFT_B200_COLSPLIT=1 selects the radix-2 pre-stage + 128 x 128 variant."""
+    monkeypatch.setenv("HPXFFT_B200_COLSPLIT", "1")
     n, width = 32768, 16 * 9 + 3
     rng = np.random.default_rng(5)
     a = rng.uniform(-1, 1, (n, width)) + 1j * rng.uniform(-1, 1, (n, width))
