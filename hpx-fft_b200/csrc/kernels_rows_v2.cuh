@@ -14,8 +14,9 @@
 // The final pass (radix 16 across the sub-sequences on paired columns + Hermitian split + transposed store) is the
 // old one with new shared-memory addresses.  CTA barriers per row: 3 instead of 6.
 //
-// Shared-memory address of element p: P(p) = p + (p >> 4) + (p >> 9) (16-byte units): conflict-free for all three
-// access patterns (lane stride 16 -> 17, lane stride 512 -> 545 = 1 mod 8, 16 contiguous per lane with lane stride 17 / 545).
+// Shared-memory address of element p (16-byte units): P(p) = p ^ (((p >> 4) ^ (p >> 9)) & 7) -- an XOR swizzle of the
+// position inside the 128-byte bank row.  Conflict-free for all access patterns (8 consecutive lanes differ in bits 4-6 or
+// 9-11 of p, or are contiguous) and, unlike padding, it keeps the staged row aligned to the bank rows.
 #pragma once
 #include "kernels_rows.cuh"
 
@@ -23,11 +24,11 @@ namespace hpxfft_b200 {
 
 namespace rv2 {
 constexpr int M = 8192, PP = 512, JW = PP / 2 + 1; // columns of the final pass; table width (mirror column uses the conjugate)
-constexpr int LP = M + (M >> 4) + (M >> 9) + 8;
-// pencil | twA[u*16+s] = w_512^(u s) | tw2[r*JW+j] = w_M^(r j) | tw3[j] = w_n^j
+constexpr int LP = M;
+// pencil | twA[s*32+u] = w_512^(u s) | tw2[r*JW+j] = w_M^(r j) | tw3[j] = w_n^j
 constexpr int TW_ENTRIES = 512 + 16 * JW + JW;
 constexpr size_t SMEM = (size_t) (LP + TW_ENTRIES) * sizeof(cd);
-__device__ __forceinline__ int pad(int p) { return p + (p >> 4) + (p >> 9); }
+__device__ __forceinline__ int pad(int p) { return p ^ (((p >> 4) ^ (p >> 9)) & 7); }
 }  // namespace rv2
 
 template <bool FASTADDR>
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
 
     // tables from tw = w_n^i, n = 2M (published by the first barrier of the row loop)
     for (int i = lt; i < 512; i += ROW_THREADS) {
-        const int u = i >> 4, s = i & 15;
+        const int s = i >> 5, u = i & 31;
         twA[i] = ldtw(tw, (unsigned) (u * s) * (unsigned) (2 * M / 512));
     }
     for (int i = lt; i < 16 * JW; i += ROW_THREADS) {
@@ -85,16 +86,18 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j1 = 2 * warp + h;
-                cd *base = sm + (j1 + 17 * u); // pad(j1 + 16 u + 512 r) = j1 + 17 u + 545 r
+                // element j1 + 16 u + 512 r sits at (that & ~7) | ((j1 ^ u ^ r) & 7)
+                cd *base = sm + ((j1 & 8) + 16 * u);
+                const int x = (j1 ^ u) & 7;
                 cd a[16];
 #pragma unroll
-                for (int r = 0; r < 16; ++r) a[r] = base[545 * r];
+                for (int r = 0; r < 16; ++r) a[r] = base[512 * r + (x ^ (r & 7))];
                 fft_dif<16>(a);
 #pragma unroll
                 for (int s = 0; s < 16; ++s) {
                     cd o = a[bitrev(s, 4)];
-                    if (s) o = cmul(o, twA[u * 16 + s]);
-                    base[545 * s] = o;
+                    if (s) o = cmul(o, twA[s * 32 + u]);
+                    base[512 * s + (x ^ (s & 7))] = o;
                 }
             }
         }
@@ -102,27 +105,29 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
         // ---- pass B: radix 32 over u for fixed s: one lane per (sub-sequence, s), in place ----
         {
             const int h = lane >> 4, s = lane & 15, j1 = 2 * warp + h;
-            cd *base = sm + (j1 + 545 * s); // pad(j1 + 16 u + 512 s) = j1 + 17 u + 545 s
+            cd *base = sm + ((j1 & 8) + 512 * s); // element j1 + 16 u + 512 s sits at (that & ~7) | ((j1 ^ u ^ s) & 7)
+            const int x = (j1 ^ s) & 7;
             cd c[32];
 #pragma unroll
-            for (int u = 0; u < 32; ++u) c[u] = base[17 * u];
+            for (int u = 0; u < 32; ++u) c[u] = base[16 * u + (x ^ (u & 7))];
             fft_dif<32>(c);
 #pragma unroll
-            for (int t = 0; t < 32; ++t) base[17 * t] = c[bitrev(t, 5)]; // F_j1[s + 16 t]
+            for (int t = 0; t < 32; ++t) base[16 * t + (x ^ (t & 7))] = c[bitrev(t, 5)]; // F_j1[s + 16 t]
         }
         __syncthreads(); // (2) all 16 sub-spectra are complete
 
         // ---- final pass: radix 16 over j1 on the paired columns jA = lt and jB = PP - lt (lt = 0: PP/2) ----
-        // column k2 = s + 16 t lives at pad(16 t + 512 s + j1) = j1 + 17 t + 545 s
         const int jA = lt, jB = lt ? PP - lt : PP / 2;
         cd A[16], B[16];
         {
-            const cd *pa = sm + (17 * (jA >> 4) + 545 * (jA & 15));
-            const cd *pb = sm + (17 * (jB >> 4) + 545 * (jB & 15));
+            // column k2 = s + 16 t, sub-sequence r: element r + 16 t + 512 s sits at (that & ~7) | ((r ^ t ^ s) & 7)
+            const cd *pa = sm + (16 * (jA >> 4) + 512 * (jA & 15));
+            const cd *pb = sm + (16 * (jB >> 4) + 512 * (jB & 15));
+            const int xa = ((jA >> 4) ^ jA) & 7, xb = ((jB >> 4) ^ jB) & 7;
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
-                A[r] = pa[r];
-                B[r] = pb[r];
+                A[r] = pa[(r & 8) + (xa ^ (r & 7))];
+                B[r] = pb[(r & 8) + (xb ^ (r & 7))];
             }
         }
         __syncthreads(); // (3) the pencil buffer is dead: refill it with the next row while this one finishes in registers
