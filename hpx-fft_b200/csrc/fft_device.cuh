@@ -141,6 +141,12 @@ __device__ __forceinline__ void st_cg(cd *p, cd v)
     asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
+// 256-bit streaming store of two adjacent complex values (sm_100: STG.E.EF.ENL2.256); p must be 32-byte aligned
+__device__ __forceinline__ void st_stream_pair(cd *p, cd v0, cd v1)
+{
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v0.x), "d"(v0.y), "d"(v1.x), "d"(v1.y) : "memory");
+}
+
 // L2 eviction-priority hints (createpolicy).  evict_last: data that is re-read soon by the same kernel (per-CTA scratch,
 // a row that the next sub-FFT reads again) must survive the flood of streaming traffic that passes through L2 in the
 // meantime; evict_first on the last use hands the lines back.

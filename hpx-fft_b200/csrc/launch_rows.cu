@@ -1,5 +1,6 @@
 // launch_rows.cu -- dispatch of the row (r2c) kernels.
 #include "kernels_rows_long.cuh"
+#include "kernels_rows_long2.cuh"
 #include "kernels_rows_v2.cuh"
 
 #include <cstdlib>
@@ -62,6 +63,27 @@ template <bool FAST> int launch_rows_v2_t(const hpxfft_b200_plan *p, const RowDs
     return 0;
 }
 
+// ny = 32768: both DIF halves in one CTA, even bins parked in L2, 256-bit paired stores (kernels_rows_long2.cuh)
+template <bool FAST> int launch_rows_long2_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+{
+    if (int rc = ensure_smem(rows_long2_kernel<FAST>, rl2::SMEM, p->device)) return rc;
+    if (!p->zraw) return fail(HPXFFT_B200_ESTATE, "long-row scratch missing");
+    const unsigned cap = (unsigned) (p->sm_count - p->sm_reserve > 0 ? p->sm_count - p->sm_reserve : 1);
+    const unsigned grid = nrows < cap ? nrows : cap;
+    rows_long2_kernel<FAST><<<grid, ROW_THREADS, rl2::SMEM, p->stream>>>(V, pitch, nrows, dst, p->tw_row, p->zraw);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int rows_long_variant()
+{
+    static const int v = [] {
+        const char *e = getenv("HPXFFT_B200_ROWS_LONG");
+        return e ? atoi(e) : 2;
+    }();
+    return v;
+}
+
 bool rows_v1_path()
 {
     static const bool v = [] {
@@ -112,7 +134,10 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
     case 8192:
         if (rows_v1_path()) return launch_rows_big<8192>(p, dst, nrows, V, pitch);
         return dst.P == 1 ? launch_rows_v2_t<true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false>(p, dst, nrows, V, pitch);
-    case 16384: return rows_old_path() ? launch_rows_big<8192, 2>(p, dst, nrows, V, pitch) : launch_rows_long<2>(p, dst, nrows, V, pitch);
+    case 16384:
+        if (rows_old_path()) return launch_rows_big<8192, 2>(p, dst, nrows, V, pitch);
+        if (rows_long_variant() != 2) return launch_rows_long<2>(p, dst, nrows, V, pitch); // HPXFFT_B200_ROWS_LONG=1: generic long-row kernel
+        return dst.P == 1 ? launch_rows_long2_t<true>(p, dst, nrows, V, pitch) : launch_rows_long2_t<false>(p, dst, nrows, V, pitch);
     case 32768: return rows_old_path() ? launch_rows_big<8192, 4>(p, dst, nrows, V, pitch) : launch_rows_long<4>(p, dst, nrows, V, pitch);
     case 65536: return rows_old_path() ? launch_rows_big<8192, 8>(p, dst, nrows, V, pitch) : launch_rows_long<8>(p, dst, nrows, V, pitch);
     default: return fail(HPXFFT_B200_EINVAL, "unsupported row length ny=%zu (ny/2 must be a power of two <= 65536)", 2 * m);
