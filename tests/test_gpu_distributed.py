@@ -39,6 +39,8 @@ def _worker(rank, world, port, q):
         oracle = entry.load_oracle()
         results = []
         cases = CASES + [(world, 32)]                       # n_x_local == 1
+        if os.environ.get("HPXFFT_B200_DIST_CASES") == "fast":   # 8-GPU box time is expensive: one case per kernel family
+            cases = [(64, 64), (1024, 2048), (64, 32768), (32768, 64), (296, 16384), (world, 32)]
         for (nx, ny) in cases:
             nxl = nx // world
             full = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=11)   # x-dependent input
