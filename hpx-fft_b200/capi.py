@@ -29,6 +29,9 @@ PROTOTYPES = {
     "hpxfft_b200_download_tile": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
     "hpxfft_b200_bench_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "hpxfft_b200_c2c_cols_variant": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int]),
+    "hpxfft_b200_upload_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hpxfft_b200_download_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hpxfft_b200_on_complete": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hpxfft_b200_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hpxfft_b200_download": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hpxfft_b200_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64]),
@@ -51,6 +54,7 @@ PROTOTYPES = {
 }
 
 _lib = None
+CALLBACK = C.CFUNCTYPE(None, C.c_void_p)   # hpxfft_b200_callback
 
 
 class Hpxfft_b200Error(RuntimeError):

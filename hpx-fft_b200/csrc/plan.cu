@@ -1236,6 +1236,30 @@ int hpxfft_b200_bench_exchange(hpxfft_b200_plan *p, int which, int reps, double 
     return 0;
 }
 
+int hpxfft_b200_upload_async(hpxfft_b200_plan *p, const double *host_slab)
+{
+    if (!p || !host_slab) return fail(HPXFFT_B200_EINVAL, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    CU(cudaMemcpyAsync(p->V, host_slab, p->nxl * p->n_col * sizeof(double), cudaMemcpyDefault, p->stream));
+    return 0;
+}
+
+int hpxfft_b200_download_async(hpxfft_b200_plan *p, double *host_slab)
+{
+    if (!p || !host_slab) return fail(HPXFFT_B200_EINVAL, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    CU(cudaMemcpyAsync(host_slab, p->V, p->nxl * p->n_col * sizeof(double), cudaMemcpyDefault, p->stream));
+    return 0;
+}
+
+int hpxfft_b200_on_complete(hpxfft_b200_plan *p, hpxfft_b200_callback fn, void *user)
+{
+    if (!p || !fn) return fail(HPXFFT_B200_EINVAL, "NULL argument");
+    CU(cudaSetDevice(p->device));
+    CU(cudaLaunchHostFunc(p->stream, fn, user));
+    return 0;
+}
+
 double hpxfft_b200_measurement(const hpxfft_b200_plan *p, const char *key)
 {
     if (!p || !key) return 0.0;

@@ -55,12 +55,31 @@ class loop:
     def get_measurement(self, name: str) -> float:
         if not self._plan:
             return 0.0
+        self._lib.hpxfft_b200_synchronize(self._plan)   # refreshes the timers of transforms that were only enqueued
         return float(self._lib.hpxfft_b200_measurement(self._plan, name.encode()))
 
     def write_plans_to_file(self, file_path: str) -> None:
         rc = self._lib.hpxfft_b200_write_plans(self._plan, file_path.encode())
         if rc != capi.OK:
             raise RuntimeError("Failed to open file: " + file_path)  # shared/loop.cpp:198-201
+
+    def fft_2d_r2c_async(self):
+        """Enqueue the transform and the copy back; returns a concurrent.futures.Future that a CUDA stream callback
+        (hpxfft_b200_on_complete) fulfils with the vector_2d -- the agas client surface, no thread waits on the GPU."""
+        from concurrent.futures import Future
+        if not self._plan or self._values is None:
+            raise RuntimeError("loop: initialize() must be called before fft_2d_r2c")
+        fut = Future()
+        out, self._values = self._values, None
+        capi.check(self._lib.hpxfft_b200_execute_async(self._plan))
+        capi.check(self._lib.hpxfft_b200_download_async(self._plan, out.data().ctypes.data))
+
+        def done(_user):
+            fut.set_result(out)
+        cb = capi.CALLBACK(done)
+        self._extra["cb"] = cb          # keep the trampoline alive until it has run
+        capi.check(self._lib.hpxfft_b200_on_complete(self._plan, cb, None))
+        return fut
 
     # extensions used by the benchmark (device-resident operation)
     def plan_handle(self) -> C.c_void_p:
@@ -76,3 +95,24 @@ class loop:
             self._destroy()
         except Exception:
             pass
+
+
+class agas:
+    """Client surface of hpxfft::shared::agas (core/include/hpxfft/shared/agas.hpp:13-27): the same two calls returning
+    futures.  initialize() (plan creation, host work) runs on a worker thread; fft_2d_r2c() only enqueues and its future
+    is fulfilled by a CUDA stream callback."""
+
+    def __init__(self, device: int = -1):
+        from concurrent.futures import ThreadPoolExecutor
+        self._loop = loop(device)
+        self._pool = ThreadPoolExecutor(max_workers=1)
+
+    def initialize(self, values_vec: vector_2d, PLAN_FLAG: str):
+        check_plan_flag(PLAN_FLAG)
+        return self._pool.submit(self._loop.initialize, values_vec, PLAN_FLAG)
+
+    def fft_2d_r2c(self):
+        return self._loop.fft_2d_r2c_async()
+
+    def get_measurement(self, name: str) -> float:
+        return self._loop.get_measurement(name)

@@ -1,8 +1,10 @@
 // hpxfft::distributed::agas -- client surface of core/include/hpxfft/distributed/agas.hpp:13-29:
 //   future<void> initialize(vector_2d, COMM_FLAG, PLAN_FLAG);   future<vector_2d> fft_2d_r2c();
 // The reference schedules one HPX action per row behind this client (core/src/distributed/agas.cpp:149-300);
-// on a GPU the whole transform is a handful of kernel launches, so the future simply wraps
-// distributed::loop.  hpx::future when built with HPX, std::future otherwise.
+// on a GPU the whole transform is a handful of kernel launches, so the client wraps distributed::loop: initialize()
+// (plan creation, communicator bootstrap: host work) runs on a worker, fft_2d_r2c() only ENQUEUES the transform and the
+// copy back and returns a future that a CUDA stream callback fulfils -- no thread waits on the GPU.
+// hpx::future when built with HPX, std::future otherwise.
 #ifndef HPXFFT_B200_DISTRIBUTED_AGAS_HPP
 #define HPXFFT_B200_DISTRIBUTED_AGAS_HPP
 
@@ -28,8 +30,12 @@ struct agas
 
     HPXFFT_B200_FUTURE<vector_2d> fft_2d_r2c()
     {
-        auto impl = impl_;
-        return HPXFFT_B200_ASYNC([impl]() { return impl->fft_2d_r2c(); });
+        if (!impl_->has_plan())  // bad COMM_FLAG: the reference prints and returns the data untouched (distributed/loop.cpp:175-179)
+        {
+            auto impl = impl_;
+            return HPXFFT_B200_ASYNC([impl]() { return impl->fft_2d_r2c(); });
+        }
+        return impl_->fft_2d_r2c_async();
     }
 
     HPXFFT_B200_FUTURE<void> initialize(vector_2d values_vec, const std::string COMM_FLAG, const std::string PLAN_FLAG)

@@ -11,6 +11,7 @@
 #define HPXFFT_B200_DISTRIBUTED_LOOP_HPP
 
 #include "../util/b200_error.hpp"
+#include "../util/stream_future.hpp"
 #include "../util/vector_2d.hpp"
 #include "bootstrap.hpp"
 
@@ -76,7 +77,23 @@ struct loop
         return std::move(values_vec_);
     }
 
-    real get_measurement(std::string name) { return plan_ ? hpxfft_b200_measurement(plan_, name.c_str()) : 0.0; }
+    // extension (agas client surface): enqueue only; the future is fulfilled by a stream callback.  Collective like fft_2d_r2c.
+    hpxfft::util::future<vector_2d> fft_2d_r2c_async()
+    {
+        if (!plan_) throw std::runtime_error("hpxfft::distributed::loop: no plan (initialize() missing or bad COMM_FLAG)");
+        hpxfft::util::b200_check(hpxfft_b200_execute_async(plan_));
+        hpxfft::util::b200_check(hpxfft_b200_download_async(plan_, values_vec_.data()));
+        return hpxfft::util::when_stream_reaches<vector_2d>(plan_, [this]() { return std::move(values_vec_); });
+    }
+
+    bool has_plan() const { return plan_ != nullptr; }
+
+    real get_measurement(std::string name)
+    {
+        if (!plan_) return 0.0;
+        hpxfft_b200_synchronize(plan_);  // refreshes the timers of transforms that were only enqueued
+        return hpxfft_b200_measurement(plan_, name.c_str());
+    }
 
     void set_device(int device) { device_ = device; }
     std::size_t this_locality() const { return boot_.this_locality; }

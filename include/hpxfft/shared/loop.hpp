@@ -9,6 +9,7 @@
 #define HPXFFT_B200_SHARED_LOOP_HPP
 
 #include "../util/b200_error.hpp"
+#include "../util/stream_future.hpp"
 #include "../util/vector_2d.hpp"
 
 #include <string>
@@ -43,7 +44,22 @@ struct loop
     vector_2d fft_2d_r2c_seq() { return run(); }
     vector_2d fft_2d_r2c() { return run(); }
 
-    real get_measurement(std::string name) { return plan_ ? hpxfft_b200_measurement(plan_, name.c_str()) : 0.0; }
+    // extension (agas client surface): the transform and the copy back are only enqueued; the future is fulfilled by a
+    // stream callback when the result has landed in the (page-locked) vector_2d storage
+    hpxfft::util::future<vector_2d> fft_2d_r2c_async()
+    {
+        if (!plan_) throw std::runtime_error("hpxfft::shared::loop: initialize() has not been called");
+        hpxfft::util::b200_check(hpxfft_b200_execute_async(plan_));
+        hpxfft::util::b200_check(hpxfft_b200_download_async(plan_, values_vec_.data()));
+        return hpxfft::util::when_stream_reaches<vector_2d>(plan_, [this]() { return std::move(values_vec_); });
+    }
+
+    real get_measurement(std::string name)
+    {
+        if (!plan_) return 0.0;
+        hpxfft_b200_synchronize(plan_);  // refreshes the timers of transforms that were only enqueued
+        return hpxfft_b200_measurement(plan_, name.c_str());
+    }
 
     void write_plans_to_file(std::string file_path)
     {

@@ -146,6 +146,17 @@ int hpxfft_b200_transform(hpxfft_b200_plan *, double *host_slab_inout);
  * directions: the download of transform i overlaps the upload of transform i+1. */
 int hpxfft_b200_transform_async(hpxfft_b200_plan *, double *host_slab_inout);
 
+/* Building blocks of a fully asynchronous round trip (the agas client surfaces, core/include/hpxfft/shared/agas.hpp:19-24,
+ * core/include/hpxfft/distributed/agas.hpp:21-26, return futures): upload_async / execute_async / download_async only
+ * ENQUEUE on the plan's stream; on_complete enqueues a host function (cudaLaunchHostFunc) that runs when everything
+ * enqueued before it has finished -- it fulfils the future without a thread blocked on the GPU.  The callback must not
+ * call back into this library or CUDA.  Host buffers should be page-locked (hpxfft_b200_host_alloc) and must stay
+ * valid until the callback has run. */
+typedef void (*hpxfft_b200_callback)(void *user);
+int hpxfft_b200_upload_async(hpxfft_b200_plan *, const double *host_slab);
+int hpxfft_b200_download_async(hpxfft_b200_plan *, double *host_slab);
+int hpxfft_b200_on_complete(hpxfft_b200_plan *, hpxfft_b200_callback fn, void *user);
+
 /* Runs exchange #1 or #2 (which = 1 | 2) ALONE `reps` times on whatever the staging buffers hold and
  * returns the average milliseconds -- the NVLink roofline of the transport without the FFT kernels.
  * Collective; the slab contents are undefined afterwards.  HPXFFT_B200_ESTATE for the fused transport. */

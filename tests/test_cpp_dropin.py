@@ -70,6 +70,12 @@ def test_cpp_shared_loop_golden(cpp_bins):
 
 
 @pytest.mark.gpu
+def test_cpp_agas_clients(cpp_bins):
+    r = run([os.path.join(cpp_bins, "test_agas")], env={"RANK": "0", "WORLD_SIZE": "1"})
+    assert r.returncode == 0 and "test_agas ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("comm", ["scatter", "all_to_all", "p2p"])
 def test_cpp_distributed_loop_one_locality(cpp_bins, comm):
     r = run([os.path.join(cpp_bins, "test_distributed_loop"), comm], env={"RANK": "0", "WORLD_SIZE": "1"})

@@ -47,6 +47,23 @@ def test_golden_distributed_agas(pkg, oracle):
     assert np.array_equal(out.data(), oracle.GOLDEN_4x4_OUT)
 
 
+def test_golden_shared_agas(pkg, oracle):
+    # test/src/test_shared_agas.cpp (plan flag "measure"); the transform future is fulfilled by a stream callback
+    fft = pkg.shared.agas(device=0)
+    fft.initialize(pkg.vector_2d.from_array(oracle.GOLDEN_4x4_IN.copy()), "measure").result()
+    fut = fft.fft_2d_r2c()
+    out = fut.result(timeout=60)
+    assert np.array_equal(out.data(), oracle.GOLDEN_4x4_OUT)
+    assert fft.get_measurement("total") >= 0.0
+    # a larger transform whose future is pending while the host goes on
+    a = oracle.make_input(1024, 4096, oracle.PATTERN_UNIFORM, seed=9)
+    fft2 = pkg.shared.agas(device=0)
+    fft2.initialize(pkg.vector_2d.from_array(a.copy()), "estimate").result()
+    fut2 = fft2.fft_2d_r2c()
+    ref = oracle.fft_2d_r2c_shared(a, workers=4)          # host work overlapping the GPU round trip
+    assert oracle.rel_l2(fut2.result(timeout=60).data(), ref) <= TOL
+
+
 # ---------------------------------------------------------------- 1-D kernels (the fftw_adapter seam)
 @pytest.mark.parametrize("ny", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072])
 def test_r2c_rows(pkg, lib, oracle, ny):
