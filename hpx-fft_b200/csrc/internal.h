@@ -55,7 +55,11 @@ struct hpxfft_b200_plan {
     unsigned n1 = 1, n2 = 1;
     unsigned col_split = 1;           // radix of the decimation-in-frequency pre-stage folded into the level-A load (nx = col_split*n1*n2)
     bool two_level = false;
-    bool rows_generic = false, cols_generic = false; // lengths that are not powers of two
+    bool rows_generic = false, cols_generic = false; // lengths that are not powers of two: direct O(n^2) DFT (small sizes only)
+    bool rows_mixed = false, cols_mixed = false;     // ... n = t*q, t odd: mixed radix (kernels_generic.cuh)
+    unsigned gen_ct = 1, gen_cq = 0;                 // column length nx = gen_ct * gen_cq
+    hpxfft_b200::cd *S1 = nullptr;                   // output of the odd-radix column pre-stage
+    hpxfft_b200_plan *colsub = nullptr;              // plan-view of the power-of-two column stage (length gen_cq, reads S1)
     // device buffers
     double *V = nullptr;              // slab, nxl x n_col doubles
     hpxfft_b200::cd *bufA = nullptr;  // send staging of exchange #1 and #2 (TR_NCCL, TR_CE)
@@ -114,6 +118,15 @@ int launch_tile(const cd *A, cd *I, unsigned n, unsigned width, cudaStream_t s);
 int launch_untile(const cd *I, cd *A, unsigned n, unsigned width, cudaStream_t s);
 int launch_rows_generic(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m);
 int launch_cols_generic(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles, unsigned nx);
+
+// n = t * q, t odd (launch_generic.cu)
+void gen_factor(size_t n, unsigned &t, unsigned &q, unsigned &lg);
+bool gen_rows_supported(size_t m);
+bool gen_cols_supported(size_t nx);
+int gen_setup_col_stage(hpxfft_b200_plan *p);
+void gen_free_col_stage(hpxfft_b200_plan *p);
+int launch_rows_mixed(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m);
+int launch_cols_mixed(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, int *launches);
 
 // exp(-2 pi i k / n), k < n, rounded from long double; exact on the axes and diagonals
 void make_twiddles(std::vector<double2> &t, size_t n);

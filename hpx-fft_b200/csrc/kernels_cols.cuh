@@ -162,10 +162,12 @@ __global__ void __launch_bounds__(col_threads(N)) cols_single_kernel(InterView i
     fill_pass_twiddles<N>(ptw, tw, 1u, (int) threadIdx.x, col_threads(N));
     if (col_npass(N) > 1) __syncthreads();
     const unsigned ct = blockIdx.x;
+    unsigned ctr, row0;
+    coldst_strip(out, ct, ctr, row0);
     auto ld = [&](int i, int c) -> cd { return ld_stream(inter_ptr(in, (unsigned) i, ct, (unsigned) c)); };
     auto st = [&](int k, int c, cd val) {
-        const unsigned kl = ct * CW + c;
-        if (kl < out.w) st_stream(coldst_ptr(out, (unsigned) k, kl), val);
+        const unsigned kl = ctr * CW + c;
+        if (kl < out.w) st_stream(coldst_ptr(out, row0 + out.vt * (unsigned) k, kl), val);
     };
     tile_fft<N>(smem, ptw, ld, st);
 }
@@ -205,9 +207,11 @@ __global__ void __launch_bounds__(col_threads(N2))
     const unsigned k1 = blockIdx.x, ct = blockIdx.y;
     const cd *Sk = S + ((unsigned long long) ct * n1 + k1) * N2 * CW;
     auto ld = [&](int i, int c) -> cd { return Sk[(unsigned) i * CW + c]; };
+    unsigned ctr, row0;
+    coldst_strip(out, ct, ctr, row0);
     auto st = [&](int k2, int c, cd val) {
-        const unsigned kl = ct * CW + c;
-        if (kl < out.w) st_stream(coldst_ptr(out, k1 + n1 * (unsigned) k2, kl), val);
+        const unsigned kl = ctr * CW + c;
+        if (kl < out.w) st_stream(coldst_ptr(out, row0 + out.vt * (k1 + n1 * (unsigned) k2), kl), val);
     };
     tile_fft<N2>(smem, ptw, ld, st);
 }
@@ -400,12 +404,15 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
             const unsigned c2 = sl % SPLIT;
             const cd *Sk = S + (unsigned long long) (sl % ctl.nslot) * slot_elems + (unsigned long long) k1 * N2 * CW;
             auto ld = [&](int i, int c) -> cd { return ld_cg(Sk + (unsigned) i * CW + c); };
+            unsigned ctr, row0;
+            coldst_strip(out, ct, ctr, row0);
             auto st = [&](int k2, int c, cd val) {
-                const unsigned kl = ct * CW + c;
+                const unsigned kl = ctr * CW + c;
+                const unsigned kx = row0 + out.vt * (c2 + (unsigned) SPLIT * (k1 + (unsigned) N1 * (unsigned) k2));
 #ifdef HPXFFT_B200_DIAG_NOSTORE_V
-                if (kl < out.w && val.x == 1.2345678e300) st_stream(coldst_ptr(out, c2 + (unsigned) SPLIT * (k1 + (unsigned) N1 * (unsigned) k2), kl), val);
+                if (kl < out.w && val.x == 1.2345678e300) st_stream(coldst_ptr(out, kx, kl), val);
 #else
-                if (kl < out.w) st_stream(coldst_ptr(out, c2 + (unsigned) SPLIT * (k1 + (unsigned) N1 * (unsigned) k2), kl), val);
+                if (kl < out.w) st_stream(coldst_ptr(out, kx, kl), val);
 #endif
             };
             tile_fft<N2>(smem, ptw2, ld, st);

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
 
 // Hermitian split as a separate pass (rows longer than 2*8192 complex): zraw[row][k], k < m  ->  X[k], k <= m.
 // grid = (nxl, ceil((m/2+1)/256))  -- rows on grid.x: a slab may have more than 65535 rows
-__global__ void herm_split_kernel(const cd *__restrict__ zraw, unsigned m, unsigned nxl, RowDst dst, const cd *__restrict__ tw)
+static __global__ void herm_split_kernel(const cd *__restrict__ zraw, unsigned m, unsigned nxl, RowDst dst, const cd *__restrict__ tw)
 {
     const unsigned row = blockIdx.x;
     const unsigned k = blockIdx.y * blockDim.x + threadIdx.x;

@@ -53,6 +53,10 @@ template <int N2> int launch_cols_B(const hpxfft_b200_plan *p, const cd *S, cons
 int launch_cols(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles, cd *S, unsigned nx, unsigned n1,
                 unsigned n2, bool two_level, int *launches, cudaEvent_t mid)
 {
+    if (p->cols_mixed) {
+        if (mid) CU(cudaEventRecord(mid, p->stream));
+        return launch_cols_mixed(p, in, out, launches);
+    }
     if (p->cols_generic) {
         if (launches) *launches += 1;
         if (mid) CU(cudaEventRecord(mid, p->stream));

@@ -1,0 +1,158 @@
+// launch_generic.cu -- lengths n = t * q with an odd factor t (kernels_generic.cuh): plan-side set-up of the power-of-two
+// stage that follows the odd-radix column pre-stage, and the launchers.
+#include "kernels_generic.cuh"
+#include "launch_util.h"
+
+#include <cstdlib>
+
+namespace hpxfft_b200 {
+
+void gen_factor(size_t n, unsigned &t, unsigned &q, unsigned &lg)
+{
+    q = 1;
+    lg = 0;
+    while (n % 2 == 0 && n > 0) {
+        n /= 2;
+        q *= 2;
+        ++lg;
+    }
+    t = (unsigned) n;
+}
+
+bool gen_rows_supported(size_t m)
+{
+    unsigned t, q, lg;
+    gen_factor(m, t, q, lg);
+    return t > 1 && t < GEN_TMAX_ROWS && m <= 8192;
+}
+
+bool gen_cols_supported(size_t nx)
+{
+    unsigned t, q, lg;
+    gen_factor(nx, t, q, lg);
+    return t > 1 && t <= GEN_TMAX_COLS && q <= (1u << 18);
+}
+
+int launch_rows_mixed(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m)
+{
+    RowsMixedArgs a;
+    gen_factor(m, a.t, a.q, a.lg);
+    const size_t smem = (m + a.t) * sizeof(cd);
+    if (int rc = ensure_smem(rows_mixed_kernel, smem, p->device)) return rc;
+    int per_sm = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_mixed_kernel, GEN_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const unsigned cap = (unsigned) (p->sm_count * per_sm);
+    const unsigned grid = nrows < cap ? nrows : cap;
+    rows_mixed_kernel<<<grid, GEN_THREADS, smem, p->stream>>>(V, pitch, nrows, dst, a, p->tw_row);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// plan-view of the power-of-two stage: a column FFT of length q over (strips * t) virtual strips that reads S1
+int gen_setup_col_stage(hpxfft_b200_plan *p)
+{
+    unsigned t, q, lg;
+    gen_factor(p->nx, t, q, lg);
+    p->gen_ct = t;
+    p->gen_cq = q;
+    CU(cudaMalloc(&p->S1, (size_t) p->ntiles * p->nx * CW * sizeof(cd)));
+    if (q == 1) return 0;
+    hpxfft_b200_plan *s = new hpxfft_b200_plan();
+    p->colsub = s;
+    s->device = p->device;
+    s->sm_count = p->sm_count;
+    s->stream = p->stream; // shared, not owned
+    s->nx = s->nxl = q;
+    s->ntiles = p->ntiles * t;
+    s->w = p->w;
+    // same decomposition rules as the main plan (plan.cu: choose_col_split)
+    if (q <= 256) {
+        s->two_level = false;
+        s->n1 = q;
+        s->n2 = 1;
+    } else {
+        s->two_level = true;
+        s->n1 = 1u << ((lg + 1) / 2);
+        s->n2 = 1u << (lg / 2);
+    }
+    std::vector<double2> tq;
+    make_twiddles(tq, q);
+    CU(cudaMalloc(&s->tw_col, tq.size() * sizeof(double2)));
+    CU(cudaMemcpy(s->tw_col, tq.data(), tq.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    if (s->two_level) {
+        std::vector<double2> w2((size_t) q);
+        for (size_t x2 = 0; x2 < s->n2; ++x2)
+            for (size_t k1 = 0; k1 < s->n1; ++k1) w2[x2 * s->n1 + k1] = tq[(k1 * x2) % q];
+        CU(cudaMalloc(&s->tw_il, w2.size() * sizeof(double2)));
+        CU(cudaMemcpy(s->tw_il, w2.data(), w2.size() * sizeof(double2), cudaMemcpyHostToDevice));
+        const char *e = getenv("HPXFFT_B200_FUSED");
+        s->fused = !(e && e[0] == '0') && fused_pair_exists(s->n1, s->n2);
+        size_t bytesS = (size_t) s->ntiles * q * CW * sizeof(cd);
+        if (s->fused) {
+            int bps = 1;
+            if (int rc = fused_blocks_per_sm(s->n1, s->n2, 1, &bps)) return rc;
+            s->fused_grid = (unsigned) (bps * s->sm_count);
+            const unsigned per_group = s->n1 + s->n2;
+            s->lag = (unsigned) ((3 * (size_t) s->fused_grid / 2 + per_group - 1) / per_group) + 1;
+            s->nslot = 2 * s->lag + 1;
+            if (s->nslot > s->ntiles) s->nslot = s->ntiles > 0 ? s->ntiles : 1;
+            bytesS = (size_t) s->nslot * q * CW * sizeof(cd);
+            CU(cudaMalloc(&s->ctl, (1 + 2 * (size_t) s->ntiles) * sizeof(unsigned)));
+        }
+        CU(cudaMalloc(&s->S, bytesS));
+    }
+    return 0;
+}
+
+void gen_free_col_stage(hpxfft_b200_plan *p)
+{
+    cudaFree(p->S1);
+    p->S1 = nullptr;
+    if (hpxfft_b200_plan *s = p->colsub) {
+        cudaFree(s->tw_col);
+        cudaFree(s->tw_il);
+        cudaFree(s->S);
+        cudaFree(s->ctl);
+        s->stream = nullptr;
+        delete s;
+        p->colsub = nullptr;
+    }
+}
+
+int launch_cols_mixed(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, int *launches)
+{
+    ColsOddArgs a;
+    a.t = p->gen_ct;
+    a.q = p->gen_cq;
+    a.nx = (unsigned) p->nx;
+    a.S1 = p->S1;
+    // x2 values per CTA: keep the tile within 48 KB and at least 256 outputs per CTA
+    unsigned xb = (48u * 1024u - a.t * (unsigned) sizeof(cd)) / (a.t * CW * (unsigned) sizeof(cd));
+    if (xb < 1) xb = 1;
+    if (xb > 16) xb = 16;
+    if (xb > a.q) xb = a.q;
+    a.xb = xb;
+    const size_t smem = ((size_t) a.t * xb * CW + a.t) * sizeof(cd);
+    if (int rc = ensure_smem(cols_odd_kernel, smem, p->device)) return rc;
+    cols_odd_kernel<<<dim3((a.q + xb - 1) / xb, p->ntiles), GEN_THREADS, smem, p->stream>>>(in, out, a, p->tw_col, a.q == 1);
+    CU(cudaGetLastError());
+    if (launches) *launches += 1;
+    if (a.q == 1) return 0;
+    const hpxfft_b200_plan *s = p->colsub;
+    InterView iv;
+    iv.base = p->S1;
+    iv.nxl = a.q;
+    iv.shift = pow2_shift(iv.nxl);
+    iv.tile_stride = (unsigned long long) a.q * CW;
+    iv.rank_stride = 0;
+    ColDst o2 = out;
+    o2.vt = a.t;
+    if (s->fused) {
+        if (launches) *launches += 1;
+        return launch_cols_fused(s, iv, o2, 0u, s->ntiles);
+    }
+    return launch_cols(s, iv, o2, s->ntiles, s->S, a.q, s->n1, s->n2, s->two_level, launches, nullptr);
+}
+
+}  // namespace hpxfft_b200

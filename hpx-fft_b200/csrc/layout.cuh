@@ -83,7 +83,22 @@ struct ColDst {
     unsigned nxl;           // rows per rank
     unsigned w;             // valid local columns on this rank
     unsigned shift;         // log2(nxl) when nxl is a power of two, else 0xffffffff
+    // odd-radix pre-stage (nx = vt * q, kernels_generic.cuh): the power-of-two kernels then run on vt "virtual strips" per
+    // real strip, virtual strip v = ct * vt + k1 holding the length-q transform whose output row k2 is global row k1 + vt * k2
+    unsigned vt;            // 1 = no pre-stage
 };
+
+// real strip and first output row of a (virtual) strip
+__device__ __forceinline__ void coldst_strip(const ColDst &d, unsigned strip, unsigned &ct, unsigned &row0)
+{
+    if (d.vt > 1) {
+        ct = strip / d.vt;
+        row0 = strip - ct * d.vt;
+    } else {
+        ct = strip;
+        row0 = 0;
+    }
+}
 
 __device__ __forceinline__ cd *coldst_ptr(const ColDst &d, unsigned kx, unsigned kl)
 {

@@ -180,6 +180,7 @@ void fill_coldst(const hpxfft_b200_plan *p, ColDst &d)
     d.nxl = (unsigned) p->nxl;
     d.shift = pow2_shift(d.nxl);
     d.w = p->w;
+    d.vt = 1;
     for (int r = 0; r < p->P; ++r) {
         if (r == p->rank) {
             d.base[r] = (cd *) p->V;
@@ -380,6 +381,7 @@ int enqueue_transform_nccl_pipelined(hpxfft_b200_plan *p)
             cdst.nxl = (unsigned) p->nxl;
             cdst.shift = pow2_shift(cdst.nxl);
             cdst.w = p->w;
+            cdst.vt = 1;
             const unsigned long long boff = (unsigned long long) P * p->nxl * col0;
             for (int r = 0; r < P; ++r) {
                 if (r == me) {
@@ -755,6 +757,7 @@ void hpxfft_b200_destroy(hpxfft_b200_plan *p)
         cudaStreamSynchronize(p->cstream);
         cudaStreamDestroy(p->cstream);
     }
+    gen_free_col_stage(p);
     cudaFree(p->bufC);
     cudaFree(p->V);
     cudaFree(p->bufA);
@@ -827,16 +830,26 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         hpxfft_b200_destroy(p);
         return rc;
     };
-    // powers of two take the Stockham kernels; any other length (FFTW accepts them all, the reference's
-    // default example is 8 x 14) takes the direct-DFT kernels, bounded to sizes where O(n^2) is sane
+    // powers of two take the Stockham kernels; n = t * q with a small odd factor t takes the mixed-radix kernels
+    // (kernels_generic.cuh; FFTW accepts every length, the reference's default example is 8 x 14 and its weak-scaling sweep
+    // runs 512 * t, t = 1..32); anything else falls back to the direct-DFT kernels, bounded to sizes where O(n^2) is sane
     constexpr size_t GENERIC_MAX = 8192;
-    p->rows_generic = !is_pow2(p->m);
-    p->cols_generic = !is_pow2(p->nx);
     if (p->ny < 2) return bail(fail(HPXFFT_B200_EINVAL, "unsupported ny=%zu", p->ny));
-    if (p->rows_generic ? p->ny > GENERIC_MAX : p->m > 65536)
-        return bail(fail(HPXFFT_B200_EINVAL, "unsupported ny=%zu: ny/2 must be a power of two <= 65536, or ny <= %zu", p->ny, GENERIC_MAX));
-    if (p->cols_generic ? p->nx > GENERIC_MAX : p->nx > (1u << 18))
-        return bail(fail(HPXFFT_B200_EINVAL, "unsupported nx=%zu: must be a power of two <= 2^18, or <= %zu", p->nx, GENERIC_MAX));
+    if (!is_pow2(p->m)) {
+        p->rows_mixed = gen_rows_supported(p->m);
+        p->rows_generic = !p->rows_mixed;
+    }
+    if (!is_pow2(p->nx)) {
+        p->cols_mixed = gen_cols_supported(p->nx);
+        p->cols_generic = !p->cols_mixed;
+    }
+    if (p->rows_generic ? p->ny > GENERIC_MAX : (!p->rows_mixed && p->m > 65536))
+        return bail(fail(HPXFFT_B200_EINVAL,
+                         "unsupported ny=%zu: ny/2 must be a power of two <= 65536, or (odd factor < 32) * 2^a <= 8192, or ny <= %zu", p->ny,
+                         GENERIC_MAX));
+    if (p->cols_generic ? p->nx > GENERIC_MAX : (!p->cols_mixed && p->nx > (1u << 18)))
+        return bail(fail(HPXFFT_B200_EINVAL, "unsupported nx=%zu: must be a power of two <= 2^18, or (odd factor <= 127) * 2^a, or <= %zu", p->nx,
+                         GENERIC_MAX));
     if (p->cy < (size_t) nranks) return bail(fail(HPXFFT_B200_EINVAL, "ny/2+1=%zu columns cannot be split over %d localities", p->cy, nranks));
 
     // column ownership: c_q = q*floor(cy/P), the last rank absorbs cy mod P
@@ -853,10 +866,11 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     p->c0 = p->c0_of[rank];
     p->ntiles = p->ntiles_of[rank];
     choose_col_split(p->nx, p->n1, p->n2, p->two_level, &p->col_split);
-    if (p->cols_generic) {
+    if (p->cols_generic || p->cols_mixed) {
         p->two_level = false;
         p->n1 = (unsigned) p->nx;
         p->n2 = 1;
+        p->col_split = 1;
     }
 
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -961,6 +975,9 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         }
     }
 
+    if (p->cols_mixed)
+        if (int rc = gen_setup_col_stage(p)) return bail(rc);
+
     // sub-slab chunks (rank-invariant: derived from quantities every rank computes identically)
     if (p->transport == TR_CE || nccl_pipelined) {
         const int want = env_int("HPXFFT_B200_CHUNKS", p->transport == TR_CE ? 4 : 1);
@@ -1024,7 +1041,17 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
              p->ny, p->m, p->m <= 16 ? "register-resident" : "shared-memory pencil", p->m <= 16 ? (int) p->m : 32);
     p->row_desc = buf;
     if (p->rows_generic) p->row_desc = "r2c rows: direct DFT (length is not a power of two)";
-    if (p->cols_generic)
+    if (p->rows_mixed) {
+        unsigned t, q, lg;
+        gen_factor(p->m, t, q, lg);
+        snprintf(buf, sizeof(buf), "r2c rows: n=%zu via half-length complex mixed radix m = %u x %u (in-place radix-4 DIF of the stride-%u sub-sequences, radix-%u combine, Hermitian split)",
+                 p->ny, t, q, t, t);
+        p->row_desc = buf;
+    }
+    if (p->cols_mixed)
+        snprintf(buf, sizeof(buf), "c2c columns: n=%zu mixed radix %u x %u (odd-radix direct DFT pre-stage, then the power-of-two column kernels on %u virtual strips per strip)",
+                 p->nx, p->gen_ct, p->gen_cq, p->gen_ct);
+    else if (p->cols_generic)
         snprintf(buf, sizeof(buf), "c2c columns: n=%zu direct DFT (length is not a power of two)", p->nx);
     else if (p->two_level)
         snprintf(buf, sizeof(buf), "c2c columns: n=%zu %sfour-step %u x %u on %d-column tiles (level A strided + twiddle, level B contiguous)%s",
@@ -1472,6 +1499,7 @@ int hpxfft_b200_c2c_cols_variant(double *host_data, size_t n, size_t width, int 
     cdst.nxl = (unsigned) n;
     cdst.shift = pow2_shift(cdst.nxl);
     cdst.w = (unsigned) width;
+    cdst.vt = 1;
     cdst.base[0] = A;
     cdst.pitch[0] = (unsigned) width;
     cdst.col0[0] = 0;

@@ -139,17 +139,38 @@ def test_small_pow2_sweep(pkg, oracle, nx, ny):
     assert oracle.rel_l2(got, ref) <= TOL
 
 
-@pytest.mark.parametrize("nx,ny", [(8, 14), (6, 10), (12, 30), (10, 16), (16, 18), (100, 200), (3, 2), (7, 1022), (1000, 64)])
+@pytest.mark.parametrize("nx,ny", [(8, 14), (6, 10), (12, 30), (10, 16), (16, 18), (100, 200), (3, 2), (7, 1022), (1000, 64),
+                                   # mixed radix (odd factor x power of two): sizes of the reference's weak-scaling sweep
+                                   # 512 * t (benchmark/shared_benchmark.sh:100-102) and their factors
+                                   (1536, 1536), (2560, 2560), (3584, 3584), (96, 24), (24, 96), (4608, 512), (512, 4608),
+                                   (5632, 5632), (6656, 256), (256, 6656), (7680, 7680), (15872, 64), (64, 15872),
+                                   (12288, 128), (128, 12288), (8704, 9728), (14336, 32), (7, 14), (62, 62)])
 def test_generic_lengths(pkg, oracle, nx, ny):
     """Lengths that are not powers of two (FFTW accepts any n; 8 x 14 is the reference example's default,
-    examples/hpxfft/shared_loop_2d.cpp:142-143) go through the direct-DFT kernels."""
+    examples/hpxfft/shared_loop_2d.cpp:142-143): mixed radix when the odd factor is small, direct DFT otherwise."""
     a = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=7)
     got, _ = shared_fft(pkg, a)
-    assert oracle.rel_l2(got, oracle.fft_2d_r2c_longdouble(a)) <= TOL
+    ref = oracle.fft_2d_r2c_longdouble(a) if nx * ny <= 1 << 20 else oracle.fft_2d_r2c_shared(a, workers=8)
+    assert oracle.rel_l2(got, ref) <= TOL
     if (nx, ny) == (8, 14):
         r = oracle.make_input(8, 14, oracle.PATTERN_RAMP)
         z, _ = shared_fft(pkg, r)
         assert z[0, 0] == 728.0 and abs(z[0, 2] + 56) < 1e-10 and abs(z[0, 3] - 245.352031) < 1e-5   # SURVEY appendix A
+
+
+@pytest.mark.parametrize("t", list(range(1, 33)))
+def test_reference_weak_sweep_sizes(pkg, lib, oracle, t):
+    """Every size of the reference's shared weak-scaling sweep, nx = ny = 512 * t, t = 1..32 (benchmark/shared_benchmark.sh:100-102,
+    sbatch_scripts/run_hpxfft_weak_shared.sh:34-42): separable input generated on the device, tile-sampled against the closed form."""
+    import sampled
+    n = 512 * t
+    plan = C.c_void_p()
+    pkg.capi.check(lib.hpxfft_b200_create(C.byref(plan), n, n + 2, 0, 1, 0, None, b"estimate", None))
+    try:
+        r = sampled.check_plan(lib, plan, n, n, 0, 1, seed=11)
+        assert (r["num"] / r["den"]) ** 0.5 <= TOL, (t, r)
+    finally:
+        lib.hpxfft_b200_destroy(plan)
 
 
 def test_x_dependence_is_real(pkg, oracle):
