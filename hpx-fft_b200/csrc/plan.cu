@@ -813,10 +813,15 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     else if (mode == MODE_SCATTER)
         p->transport = TR_NCCL;
     else {
+        // all_to_all: the fastest correct transport for the slab at hand (measured on 8 x B200, profiles/r2_n8_bench_*.json):
+        // peer stores fused into the FFT kernels (3.56 ms per 32768^2 vs 4.90 copy-engine, 6.53 NCCL) -- unless a slab row is so long
+        // that consecutive destination rows of the column kernel's 256-byte peer stores fall into different 2 MB pages
+        // (131072^2: 1188 ms fused vs 98.8 ms copy-engine), where the chunked copy-engine exchange is the default.
         const char *e = getenv("HPXFFT_B200_A2A");
         if (e && !strcmp(e, "nccl")) p->transport = TR_NCCL;
         else if (e && !strcmp(e, "fused")) p->transport = TR_FUSED;
-        else p->transport = TR_CE;
+        else if (e && !strcmp(e, "ce")) p->transport = TR_CE;
+        else p->transport = (n_col / 2) * sizeof(cd) <= (size_t) 512 * 1024 ? TR_FUSED : TR_CE;
     }
     // dimension inference: core/src/shared/loop.cpp:163-165, core/src/distributed/loop.cpp:284-287
     p->nxl = n_x_local;

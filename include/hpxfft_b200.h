@@ -86,11 +86,13 @@ int hpxfft_b200_partition(size_t cy, int nranks, int rank, size_t *c0, size_t *w
  *                              (scatter_to / scatter_from on P communicators, distributed/loop.cpp:39-69,158-167);
  *               "all_to_all" = one personalised all-to-all per exchange (distributed/loop.cpp:72-84).  Its
  *                              transport is chosen by the environment variable HPXFFT_B200_A2A:
- *                              "ce" (default)  copy-engine peer copies over the IPC windows, cut into sub-slab
- *                                              chunks that overlap the FFT kernels, landing exchange #2
- *                                              directly in the destination slab;
+ *                              "fused"         the FFT kernels store straight into the owners' windows over NVLink: the
+ *                                              exchange overlaps the producing kernel tile by tile, no staging buffer, no
+ *                                              unpack pass (default while a slab row is at most 512 KB, i.e. ny <= 65536);
+ *                              "ce"            copy-engine peer copies over the IPC windows, cut into sub-slab chunks that
+ *                                              overlap the FFT kernels, landing exchange #2 directly in the destination slab
+ *                                              (default for longer rows, e.g. 131072^2);
  *                              "nccl"          one grouped ncclSend/ncclRecv exchange + unpack kernel;
- *                              "fused"         same as "p2p";
  *               "p2p"        = the FFT kernels store straight into the owners' windows over NVLink.
  *               Plans whose hpxfft_b200_ipc_count() is non-zero need the export / all-gather / import
  *               handshake below before the first execute.
