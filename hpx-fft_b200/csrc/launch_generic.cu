@@ -38,7 +38,8 @@ int launch_rows_mixed(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nro
     RowsMixedArgs a;
     gen_factor(m, a.t, a.q, a.lg);
     const size_t smem = (m + a.t) * sizeof(cd);
-    if (int rc = ensure_smem(rows_mixed_kernel, smem, p->device)) return rc;
+    // the attribute is set once per device for the largest row this kernel accepts (the footprint varies with m)
+    if (int rc = ensure_smem(rows_mixed_kernel, (size_t) (8192 + GEN_TMAX_ROWS) * sizeof(cd), p->device)) return rc;
     int per_sm = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_mixed_kernel, GEN_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
@@ -133,8 +134,7 @@ int launch_cols_mixed(const hpxfft_b200_plan *p, const InterView &in, const ColD
     if (xb > 16) xb = 16;
     if (xb > a.q) xb = a.q;
     a.xb = xb;
-    const size_t smem = ((size_t) a.t * xb * CW + a.t) * sizeof(cd);
-    if (int rc = ensure_smem(cols_odd_kernel, smem, p->device)) return rc;
+    const size_t smem = ((size_t) a.t * xb * CW + a.t) * sizeof(cd); // <= 48 KB by construction of xb: no opt-in needed
     cols_odd_kernel<<<dim3((a.q + xb - 1) / xb, p->ntiles), GEN_THREADS, smem, p->stream>>>(in, out, a, p->tw_col, a.q == 1);
     CU(cudaGetLastError());
     if (launches) *launches += 1;
