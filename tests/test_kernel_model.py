@@ -36,3 +36,54 @@ def test_four_step_column_fft(n1, n2, p1, p2):             # kernels_cols.cuh: l
     rng = np.random.default_rng(n1 * n2)
     x = rng.standard_normal(n1 * n2) + 1j * rng.standard_normal(n1 * n2)
     assert np.abs(mk.col_two_level(x, n1, n2, p1, p2) - np.fft.fft(x)).max() < 1e-11 * n1 * n2
+
+
+# ---------------------------------------------------------------- round-2 kernels
+def test_swizzle_is_a_permutation_and_conflict_free():        # kernels_rows_v2.cuh: rv2::pad
+    pos = [mk.swizzle(p) for p in range(8192)]
+    assert sorted(pos) == list(range(8192))
+    # 8 consecutive lanes (one quarter-warp of a 128-bit access) must hit 8 different 16-byte bank groups in each access pattern
+    for j1 in (0, 5, 15):
+        for r in (0, 3, 15):
+            assert len({mk.swizzle(j1 + 16 * u + 512 * r) & 7 for u in range(8)}) == 8            # pass A: lanes = u
+            assert len({mk.swizzle(j1 + 16 * r + 512 * s) & 7 for s in range(8)}) == 8            # pass B / final pass: lanes = s
+    assert all(mk.swizzle(p) >> 3 == p >> 3 for p in range(8192))                               # stays inside its 128-byte row
+
+
+@pytest.mark.parametrize("m", [512, 1024])
+def test_rows_v2_core(m):                                      # kernels_rows_v2.cuh with 16 x (m/16) instead of 16 x 512
+    rng = np.random.default_rng(m)
+    z = rng.standard_normal(m) + 1j * rng.standard_normal(m)
+    assert np.abs(mk.rows_v2_model(z) - np.fft.fft(z)).max() < 1e-11 * m
+
+
+@pytest.mark.parametrize("n", [64, 256, 1024])
+def test_rows_long2_parked_even_bins_and_pairs(n):             # kernels_rows_long2.cuh
+    x = np.random.default_rng(n).standard_normal(n)
+    assert np.abs(mk.rows_long2_model(x) - np.fft.rfft(x)).max() < 1e-11 * n
+    z = x[0::2] + 1j * x[1::2]
+    assert np.abs(mk.herm_split(np.fft.fft(z), n) - np.fft.rfft(x)).max() < 1e-11 * n
+
+
+@pytest.mark.parametrize("t,q", [(7, 1), (3, 2), (5, 8), (3, 64), (13, 16), (31, 32), (9, 128)])
+def test_mixed_radix_rows(t, q):                               # kernels_generic.cuh: rows_mixed_kernel
+    m = t * q
+    rng = np.random.default_rng(m)
+    z = rng.standard_normal(m) + 1j * rng.standard_normal(m)
+    assert np.abs(mk.rows_mixed_model(z, t) - np.fft.fft(z)).max() < 1e-11 * m
+    lg = q.bit_length() - 1
+    assert sorted(mk.gen_rev(k, q, lg) for k in range(q)) == list(range(q))
+
+
+@pytest.mark.parametrize("t,q", [(7, 1), (3, 4), (31, 16), (5, 64)])
+def test_mixed_radix_columns(t, q):                            # kernels_generic.cuh: cols_odd_kernel + virtual strips
+    nx = t * q
+    rng = np.random.default_rng(nx + 1)
+    y = rng.standard_normal(nx) + 1j * rng.standard_normal(nx)
+    assert np.abs(mk.cols_mixed_model(y, t) - np.fft.fft(y)).max() < 1e-11 * nx
+
+
+def test_column_prestage_split2():                             # kernels_cols.cuh: SPLIT = 2
+    rng = np.random.default_rng(3)
+    y = rng.standard_normal(512) + 1j * rng.standard_normal(512)
+    assert np.abs(mk.cols_split2_model(y, 16, 16) - np.fft.fft(y)).max() < 1e-10

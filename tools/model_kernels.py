@@ -109,3 +109,144 @@ if __name__ == "__main__":
     for n1, n2, p1, p2 in [(16, 16, [16], [16]), (32, 16, [8, 4], [16]), (8, 64, [8], [8, 8])]:
         x = rng.standard_normal(n1 * n2) + 1j * rng.standard_normal(n1 * n2)
         print("2lvl", n1, n2, np.abs(col_two_level(x, n1, n2, p1, p2) - np.fft.fft(x)).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2 kernels
+# ---------------------------------------------------------------------------------------------------------------------
+def w(n, e):
+    return np.exp(-2j * np.pi * (e % n) / n)
+
+
+def swizzle(p):
+    """kernels_rows_v2.cuh: position of element p inside the shared-memory pencil (16-byte units)."""
+    return p ^ (((p >> 4) ^ (p >> 9)) & 7)
+
+
+def rows_v2_model(z, nsub=16):
+    """kernels_rows_v2.cuh: m = nsub x (m/nsub); warp-local in-place DIF (radix 16 then radix q/16) of the stride-nsub
+    sub-sequences in a swizzled pencil, then the radix-nsub pass across the sub-sequences.  Returns Z = FFT(z)."""
+    m = len(z)
+    q = m // nsub                      # 512 for m = 8192
+    ra, rb = 16, q // 16               # pass A radix 16 over stride rb, pass B radix rb
+    sm = np.zeros(m + 8, complex)
+    for p in range(m):
+        sm[swizzle(p)] = z[p]
+    for j1 in range(nsub):             # pass A
+        for u in range(rb):
+            pos = [swizzle(j1 + nsub * (u + rb * r)) for r in range(ra)]
+            a = sm[pos]
+            b = np.array([sum(w(ra, r * s) * a[r] for r in range(ra)) * w(q, u * s) for s in range(ra)])
+            sm[pos] = b
+    for j1 in range(nsub):             # pass B
+        for s in range(ra):
+            pos = [swizzle(j1 + nsub * (u + rb * s)) for u in range(rb)]
+            c = sm[pos]
+            sm[pos] = np.array([sum(w(rb, u * t) * c[u] for u in range(rb)) for t in range(rb)])
+    Z = np.zeros(m, complex)
+    for k2 in range(q):                # final pass: F_j1[k2] at j1 + nsub*(t + rb*s), k2 = s + 16 t
+        s, t = k2 % ra, k2 // ra
+        f = np.array([sm[swizzle(j1 + nsub * (t + rb * s))] * w(m, j1 * k2) for j1 in range(nsub)])
+        for k1 in range(nsub):
+            Z[k2 + q * k1] = sum(w(nsub, j1 * k1) * f[j1] for j1 in range(nsub))
+    return Z
+
+
+def herm_split(Z, n):
+    """X[k] = E[k] - i w_n^k O[k], k = 0..m, from the half-length spectrum Z (m = n/2)."""
+    m = n // 2
+    X = np.zeros(m + 1, complex)
+    for k in range(m + 1):
+        a, b = Z[k % m], np.conj(Z[(m - k) % m])
+        X[k] = 0.5 * (a + b) - 0.5j * w(n, k) * (a - b)
+    return X
+
+
+def rows_long2_model(x):
+    """kernels_rows_long2.cuh: two DIF halves of a long row; the even half parks X[2 k2], the odd half produces X[2 k2 + 1] for
+    the same k2 and both leave as one pair.  Returns the r2c spectrum X[0..m]."""
+    n = len(x)
+    m = n // 2
+    M = m // 2
+    z = x[0::2] + 1j * x[1::2]
+    y0 = z[:M] + z[M:]
+    y1 = (z[:M] - z[M:]) * np.array([w(m, j) for j in range(M)])
+    Z0, Z1 = np.fft.fft(y0), np.fft.fft(y1)           # Z[2 k2], Z[2 k2 + 1]
+    out = np.zeros(m + 1, complex)
+    parked = np.zeros(M + 1, complex)
+    for k2 in range(M + 1):                           # even half: partner of k2 is M - k2
+        a, b = Z0[k2 % M], np.conj(Z0[(M - k2) % M])
+        parked[k2] = 0.5 * (a + b) - 0.5j * w(n, 2 * k2) * (a - b)
+    for k2 in range(M):                               # odd half: partner of k2 is M - 1 - k2; emit the pair (2 k2, 2 k2 + 1)
+        a, b = Z1[k2], np.conj(Z1[M - 1 - k2])
+        out[2 * k2] = parked[k2]
+        out[2 * k2 + 1] = 0.5 * (a + b) - 0.5j * w(n, 2 * k2 + 1) * (a - b)
+    out[m] = parked[M]
+    return out
+
+
+def gen_rev(k, q, lg):
+    """kernels_generic.cuh: position of F[k] after the in-place DIF passes (radix 4 ..., one radix 2 when lg is odd)."""
+    pos, length = 0, q
+    for _ in range(lg // 2):
+        length >>= 2
+        pos += (k & 3) * length
+        k >>= 2
+    if lg & 1:
+        pos += k & 1
+    return pos
+
+
+def rows_mixed_model(z, t):
+    """kernels_generic.cuh: m = t * q; in-place radix-4 DIF FFT_q of the stride-t sub-sequences, radix-t combine."""
+    m = len(z)
+    q = m // t
+    lg = q.bit_length() - 1
+    sm = np.array(z, complex)
+    length = q
+    for _ in range(lg // 2):
+        quarter = length // 4
+        for j1 in range(t):
+            for b in range(q // 4):
+                blk, i = divmod(b, quarter)
+                pos = [j1 + t * (blk * length + i + r * quarter) for r in range(4)]
+                a = sm[pos]
+                y = np.array([sum(w(4, r * s) * a[r] for r in range(4)) * w(length, i * s) for s in range(4)])
+                sm[pos] = y
+        length = quarter
+    if lg & 1:
+        for j1 in range(t):
+            for b in range(q // 2):
+                p0, p1 = j1 + t * 2 * b, j1 + t * (2 * b + 1)
+                a0, a1 = sm[p0], sm[p1]
+                sm[p0], sm[p1] = a0 + a1, a0 - a1
+    Z = np.zeros(m, complex)
+    for k2 in range(q):
+        slot = t * gen_rev(k2, q, lg)
+        f = np.array([sm[slot + j1] * w(m, j1 * k2) for j1 in range(t)])
+        for k1 in range(t):
+            Z[k2 + q * k1] = sum(w(t, j1 * k1) * f[j1] for j1 in range(t))
+    return Z
+
+
+def cols_mixed_model(y, t):
+    """kernels_generic.cuh: nx = t * q; odd-radix pre-stage A[k1][x2] = w_nx^(k1 x2) sum_x1 w_t^(x1 k1) y[x1 q + x2], then a
+    length-q transform per k1 whose output k2 is row k1 + t k2 (ColDst::vt)."""
+    nx = len(y)
+    q = nx // t
+    out = np.zeros(nx, complex)
+    for k1 in range(t):
+        a = np.array([w(nx, k1 * x2) * sum(w(t, x1 * k1) * y[x1 * q + x2] for x1 in range(t)) for x2 in range(q)])
+        out[k1 + t * np.arange(q)] = np.fft.fft(a)
+    return out
+
+
+def cols_split2_model(y, n1, n2):
+    """kernels_cols.cuh, SPLIT = 2: radix-2 DIF pre-stage folded into the level-A load, rows kx = c2 + 2 k'."""
+    nx = len(y)
+    h = nx // 2
+    out = np.zeros(nx, complex)
+    for c2 in range(2):
+        yc = (y[:h] + y[h:]) if c2 == 0 else (y[:h] - y[h:]) * np.array([w(nx, x) for x in range(h)])
+        out[c2 + 2 * np.arange(h)] = np.fft.fft(yc)
+    return out
