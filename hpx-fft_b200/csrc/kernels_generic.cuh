@@ -84,26 +84,30 @@ struct RowsMixedArgs {
     unsigned t, q, lg; // m = t * q, q = 2^lg
 };
 
-__global__ void __launch_bounds__(GEN_THREADS, 1)
+// TT: compile-time bound of the odd factor (inputs of one combine live in TT registers); NT threads per CTA
+template <int TT, int NT>
+__global__ void __launch_bounds__(NT, 1)
     rows_mixed_kernel(const cd *__restrict__ V, unsigned pitch, unsigned nxl, RowDst dst, RowsMixedArgs a, const cd *__restrict__ tw)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned t = a.t, q = a.q, m = t * q;
     cd *sm = reinterpret_cast<cd *>(smem_raw);
     cd *wt = sm + m; // w_t^i
+    cd *wq = wt + t; // w_q^e (twiddles of the radix-4 passes)
     const unsigned tid = threadIdx.x;
     // tw = w_n^i, n = 2 m:  w_t^i = w_n^(2 q i),  w_q^i = w_n^(2 t i),  w_m^i = w_n^(2 i)
-    for (unsigned i = tid; i < t; i += GEN_THREADS) wt[i] = ldtw(tw, 2u * q * i);
+    for (unsigned i = tid; i < t; i += NT) wt[i] = ldtw(tw, 2u * q * i);
+    for (unsigned i = tid; i < q; i += NT) wq[i] = ldtw(tw, 2u * t * i);
     for (unsigned row = blockIdx.x; row < nxl; row += gridDim.x) {
         const cd *zrow = V + (unsigned long long) row * pitch;
         __syncthreads(); // previous row's split has finished reading the pencil (and wt is published)
-        for (unsigned p = tid; p < m; p += GEN_THREADS) sm[p] = ld_stream(zrow + p);
+        for (unsigned p = tid; p < m; p += NT) sm[p] = ld_stream(zrow + p);
         __syncthreads();
         // ---- FFT_q of the t sub-sequences (stride t), in place, DIF ----
         unsigned len = q;
         for (unsigned pass = 0; pass < a.lg / 2; ++pass) {
             const unsigned quarter = len >> 2, tws = q / len; // w_len^e = w_q^(e tws)
-            for (unsigned idx = tid; idx < t * (q >> 2); idx += GEN_THREADS) {
+            for (unsigned idx = tid; idx < t * (q >> 2); idx += NT) {
                 const unsigned j1 = idx % t, b = idx / t;
                 const unsigned blk = b / quarter, i = b - blk * quarter;
                 cd *p0 = sm + j1 + (size_t) t * (blk * len + i);
@@ -113,10 +117,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1)
                 const cd md13 = make_double2(d13.y, -d13.x); // -i * d13
                 cd y0 = cadd(s02, s13), y1 = cadd(d02, md13), y2 = csub(s02, s13), y3 = csub(d02, md13);
                 if (i) {
-                    const unsigned e = 2u * t * tws * i; // index of w_len^i in w_n
-                    y1 = cmul(y1, ldtw(tw, e));
-                    y2 = cmul(y2, ldtw(tw, 2u * e));
-                    y3 = cmul(y3, ldtw(tw, 3u * e));
+                    const unsigned e = tws * i; // w_len^i = w_q^(tws i), 3 e < q
+                    y1 = cmul(y1, wq[e]);
+                    y2 = cmul(y2, wq[2u * e]);
+                    y3 = cmul(y3, wq[3u * e]);
                 }
                 p0[0] = y0;
                 p0[st] = y1;
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1)
             len = quarter;
         }
         if (a.lg & 1u) { // len == 2
-            for (unsigned idx = tid; idx < t * (q >> 1); idx += GEN_THREADS) {
+            for (unsigned idx = tid; idx < t * (q >> 1); idx += NT) {
                 const unsigned j1 = idx % t, b = idx / t;
                 cd *p0 = sm + j1 + (size_t) t * (2u * b);
                 const cd a0 = p0[0], a1 = p0[t];
@@ -138,11 +142,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1)
         }
         // ---- radix-t combine: Z[k2 + q k1] = sum_j1 w_t^(j1 k1) (w_m^(j1 k2) F_j1[k2]), in place over the t slots of k2 ----
         if (t > 1) {
-            for (unsigned k2 = tid; k2 < q; k2 += GEN_THREADS) {
+            for (unsigned k2 = tid; k2 < q; k2 += NT) {
                 cd *slot = sm + (size_t) t * gen_rev(k2, q, a.lg);
-                cd in[GEN_TMAX_ROWS];
+                cd in[TT];
 #pragma unroll
-                for (int j1 = 0; j1 < GEN_TMAX_ROWS; ++j1) {
+                for (int j1 = 0; j1 < TT; ++j1) {
                     in[j1] = make_double2(0.0, 0.0);
                     if ((unsigned) j1 < t) {
                         in[j1] = slot[j1];
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1)
                     double re = 0.0, im = 0.0;
                     unsigned e = 0;
 #pragma unroll
-                    for (int j1 = 0; j1 < GEN_TMAX_ROWS; ++j1) {
+                    for (int j1 = 0; j1 < TT; ++j1) {
                         if ((unsigned) j1 < t) {
                             const cd w = wt[e];
                             re += in[j1].x * w.x - in[j1].y * w.y;
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1)
             const unsigned k1 = k / q, k2 = k - k1 * q;
             return sm[k1 + (size_t) t * gen_rev(k2, q, a.lg)];
         };
-        for (unsigned k = tid; k <= m / 2; k += GEN_THREADS) {
+        for (unsigned k = tid; k <= m / 2; k += NT) {
             if (k == 0) {
                 const cd z0 = zat(0);
                 *rowdst_ptr(dst, row, 0u) = make_double2(z0.x + z0.y, 0.0);

@@ -33,21 +33,31 @@ bool gen_cols_supported(size_t nx)
     return t > 1 && t <= GEN_TMAX_COLS && q <= (1u << 18);
 }
 
+template <int TT, int NT>
+int launch_rows_mixed_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, const RowsMixedArgs &a)
+{
+    const size_t m = (size_t) a.t * a.q;
+    const size_t smem = (m + a.t + a.q) * sizeof(cd);
+    // the attribute is set once per device for the largest row this kernel accepts (the footprint varies with m): m <= 8192, q <= m / 3
+    if (int rc = ensure_smem(rows_mixed_kernel<TT, NT>, (size_t) (8192 + GEN_TMAX_ROWS + 8192 / 3 + 1) * sizeof(cd), p->device)) return rc;
+    int per_sm = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_mixed_kernel<TT, NT>, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    const unsigned cap = (unsigned) (p->sm_count * per_sm);
+    const unsigned grid = nrows < cap ? nrows : cap;
+    rows_mixed_kernel<TT, NT><<<grid, NT, smem, p->stream>>>(V, pitch, nrows, dst, a, p->tw_row);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int launch_rows_mixed(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m)
 {
     RowsMixedArgs a;
     gen_factor(m, a.t, a.q, a.lg);
-    const size_t smem = (m + a.t) * sizeof(cd);
-    // the attribute is set once per device for the largest row this kernel accepts (the footprint varies with m)
-    if (int rc = ensure_smem(rows_mixed_kernel, (size_t) (8192 + GEN_TMAX_ROWS) * sizeof(cd), p->device)) return rc;
-    int per_sm = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_mixed_kernel, GEN_THREADS, smem));
-    if (per_sm < 1) per_sm = 1;
-    const unsigned cap = (unsigned) (p->sm_count * per_sm);
-    const unsigned grid = nrows < cap ? nrows : cap;
-    rows_mixed_kernel<<<grid, GEN_THREADS, smem, p->stream>>>(V, pitch, nrows, dst, a, p->tw_row);
-    CU(cudaGetLastError());
-    return 0;
+    if (a.t <= 3) return launch_rows_mixed_t<4, 512>(p, dst, nrows, V, pitch, a);
+    if (a.t <= 7) return launch_rows_mixed_t<8, 512>(p, dst, nrows, V, pitch, a);
+    if (a.t <= 15) return launch_rows_mixed_t<16, 512>(p, dst, nrows, V, pitch, a);
+    return launch_rows_mixed_t<32, 256>(p, dst, nrows, V, pitch, a);
 }
 
 // plan-view of the power-of-two stage: a column FFT of length q over (strips * t) virtual strips that reads S1
