@@ -233,7 +233,6 @@ struct FusedCtl {
     unsigned lag, nslot;
     unsigned discard; // level-B tiles discard their scratch lines from L2 after reading them
     unsigned ct0;     // first strip of this launch (chunked column pass); counters / ring slots are launch-local
-    unsigned prefetch; // level-A input of the next claimed tile is prefetched into L2
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
@@ -338,7 +337,6 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
     // simultaneously (i) orders this tile's stores before its completion signal, (ii) frees the tile buffer
     // and (iii) publishes the next tile id that thread 0 wrote just before it.
     __shared__ unsigned s_ready;
-    __shared__ unsigned s_next; // the tile after s_tile (already claimed): its level-A input is prefetched into L2 one tile ahead
     unsigned t_cur = 0, t_next = 0, dep_target = 0;
     const unsigned *dep_ptr = nullptr;
     if (threadIdx.x == 0) {
@@ -348,28 +346,12 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
         if (dep_ptr)
             while (ld_acquire_u32(dep_ptr) < dep_target) __nanosleep(64);
         s_tile = t_cur;
-        s_next = t_next;
         s_ready = 1u;
     }
     __syncthreads();
     for (;;) {
         const unsigned t = s_tile;
         if (t >= total) break;
-        if (ctl.prefetch) {
-            // level-A tile one step ahead: N1 segments of CW*16 bytes = 2 lines each
-            const unsigned tn = s_next;
-            if (tn < total) {
-                const unsigned gn = tn / PER_GROUP, rn = tn - gn * PER_GROUP;
-                if (rn < (unsigned) N2 && gn < ntiles) {
-                    const unsigned ctn = ctl.ct0 + gn / SPLIT;
-                    for (int i = threadIdx.x; i < N1 * (int) SPLIT; i += NT) {
-                        const char *p = reinterpret_cast<const char *>(inter_ptr(in, (unsigned) i * N2 + rn, ctn, 0u));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
-                    }
-                }
-            }
-        }
         unsigned t_nn = 0, next_seen = 0, next_target = 0;
         const unsigned *next_ptr = nullptr;
         if (threadIdx.x == 0) {
@@ -451,7 +433,6 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
         // slow path below -- thread 0 must never spin while it still owes this tile's completion signal
         if (threadIdx.x == 0) {
             s_tile = t_next;
-            s_next = t_nn;
             s_ready = (!next_ptr || next_seen >= next_target) ? 1u : 0u;
         }
         __syncthreads();

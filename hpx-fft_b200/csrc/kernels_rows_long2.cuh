@@ -83,12 +83,6 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
         const unsigned row = row0;
 #endif
         const cd *zrow = V + (unsigned long long) row * pitch;
-        // pull the next row from HBM into L2 while this one is transformed (its first-pass loads then hit L2)
-        if (row0 + gridDim.x < nxl) {
-            const cd *nxt = V + (unsigned long long) (row0 + gridDim.x) * pitch;
-#pragma unroll
-            for (int i = 0; i < (int) (MM / 8) / ROW_THREADS; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (i * ROW_THREADS + lt) * 8));
-        }
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
             cd v[ROW_PT];
@@ -193,6 +187,13 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
                 for (int s = 0; s < 16; ++s) emit_pair(row, (unsigned) (M - 1 - (jA + s * PP)), EA[s], XM[s]);
                 if (lt == 0) st_stream(out_ptr(row, MM), ld_cg_hint(xe + M, keep)); // Nyquist bin
             }
+        }
+        // pull the next row into L2 while the CTA drains (issued here it is free; at the start of the row it queues behind the
+        // row's own loads and costs 16 %)
+        if (row0 + gridDim.x < nxl) {
+            const cd *nxt = V + (unsigned long long) (row0 + gridDim.x) * pitch;
+#pragma unroll
+            for (int i = 0; i < (int) (MM / 8) / ROW_THREADS; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (i * ROW_THREADS + lt) * 8));
         }
     }
 }

@@ -77,13 +77,6 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
 #else
         const unsigned row = row0;
 #endif
-        // Pull the NEXT row from HBM into L2 now: its cp.async refill (issued ~3/4 of a row period later, confined to the short
-        // register-only tail of this row) then streams from L2 instead of waiting for HBM at the SM's fair share of the bandwidth
-        if (row0 + gridDim.x < nxl) {
-            const cd *nxt = row_ptr(row0 + gridDim.x);
-#pragma unroll
-            for (int i = 0; i < (M / 8) / ROW_THREADS; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (i * ROW_THREADS + lt) * 8));
-        }
         cp_async_wait_all();
         __syncthreads(); // (1) the whole row has landed and is visible to every warp
 

@@ -59,13 +59,6 @@ int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const Co
         // peer destinations: keep the level-B signal fence-free (kernels_cols.cuh) at the price of writing the dead scratch lines back
         ctl.discard = (p->transport == TR_FUSED && p->P > 1) ? 0u : (unsigned) discard;
     }
-    {
-        static const int pf = [] {
-            const char *e = getenv("HPXFFT_B200_COLPF");
-            return (e && e[0] == '0') ? 0 : 1;
-        }();
-        ctl.prefetch = (unsigned) pf;
-    }
     cols_fused_kernel<N1, N2, SPLIT><<<p->fused_grid, fused_threads<N1, N2>(), smem, p->stream>>>(in, p->S, out, p->tw_col, p->tw_il, ntiles, ctl);
     CU(cudaGetLastError());
     return 0;
