@@ -63,6 +63,21 @@ class loop:
         if rc != capi.OK:
             raise RuntimeError("Failed to open file: " + file_path)  # shared/loop.cpp:198-201
 
+    def initialize_device(self, device_ptr: int, n_row: int, n_col: int, PLAN_FLAG: str) -> None:
+        """Extension: the slab already lives on the GPU (e.g. `tensor.data_ptr()` of a float64 CUDA tensor in the
+        vector_2d layout); nothing crosses PCIe.  Pair with fft_2d_r2c_device()."""
+        check_plan_flag(PLAN_FLAG)
+        self._destroy()
+        self._values = None
+        capi.check(self._lib.hpxfft_b200_create(C.byref(self._plan), n_row, n_col, 0, 1, self._device, None, PLAN_FLAG.encode(), None))
+        capi.check(self._lib.hpxfft_b200_upload(self._plan, device_ptr))
+
+    def fft_2d_r2c_device(self, device_out_ptr: int) -> None:
+        if not self._plan:
+            raise RuntimeError("loop: initialize() must be called before fft_2d_r2c")
+        capi.check(self._lib.hpxfft_b200_execute(self._plan))
+        capi.check(self._lib.hpxfft_b200_download(self._plan, device_out_ptr))
+
     def fft_2d_r2c_async(self):
         """Enqueue the transform and the copy back; returns a concurrent.futures.Future that a CUDA stream callback
         (hpxfft_b200_on_complete) fulfils with the vector_2d -- the agas client surface, no thread waits on the GPU."""

@@ -39,6 +39,24 @@ struct loop
         hpxfft::util::b200_check(hpxfft_b200_upload(plan_, values_vec_.data()));
     }
 
+    // extension: the data already lives on the GPU.  `device_slab` is a device pointer to n_row x n_col doubles in the
+    // vector_2d layout; nothing crosses PCIe.  Pair with fft_2d_r2c_device().
+    void initialize_device(const real *device_slab, std::size_t n_row, std::size_t n_col, const std::string PLAN_FLAG)
+    {
+        hpxfft::util::check_plan_flag(PLAN_FLAG);
+        reset();
+        hpxfft::util::b200_check(hpxfft_b200_create(&plan_, n_row, n_col, 0, 1, device_, nullptr, PLAN_FLAG.c_str(), nullptr));
+        hpxfft::util::b200_check(hpxfft_b200_upload(plan_, device_slab));  // device-to-device (unified addressing)
+    }
+    // transforms and writes the result to `device_out` (may equal the input pointer); reusable: call again after another
+    // hpxfft_b200_upload / initialize_device
+    void fft_2d_r2c_device(real *device_out)
+    {
+        if (!plan_) throw std::runtime_error("hpxfft::shared::loop: initialize() has not been called");
+        hpxfft::util::b200_check(hpxfft_b200_execute(plan_));
+        hpxfft::util::b200_check(hpxfft_b200_download(plan_, device_out));
+    }
+
     vector_2d fft_2d_r2c_par() { return run(); }
     // the reference's _seq differs only in CPU scheduling; on the GPU both run the same kernels
     vector_2d fft_2d_r2c_seq() { return run(); }

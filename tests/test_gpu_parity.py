@@ -351,3 +351,18 @@ def test_download_tile_and_device_pointer_upload(pkg, lib, oracle):
     finally:
         lib.hpxfft_b200_destroy(plan)
         lib.hpxfft_b200_destroy(plan2)
+
+
+def test_initialize_from_device_memory(pkg, oracle):
+    """initialize from / return to device memory (a torch CUDA tensor in the vector_2d layout), no PCIe."""
+    import torch
+    nx, ny = 256, 2048
+    a = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=21)
+    t = torch.from_numpy(a).cuda()
+    out = torch.empty_like(t)
+    fft = pkg.shared.loop(device=0)
+    fft.initialize_device(t.data_ptr(), nx, ny + 2, "estimate")
+    fft.fft_2d_r2c_device(out.data_ptr())
+    torch.cuda.synchronize()
+    assert oracle.rel_l2(out.cpu().numpy(), oracle.fft_2d_r2c_shared(a)) <= TOL
+    assert torch.equal(t.cpu(), torch.from_numpy(a))       # the caller's input tensor is untouched
