@@ -69,6 +69,19 @@ def test_cpp_shared_loop_golden(cpp_bins):
     assert r.returncode == 0 and "test_shared_loop ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_cpp_hpx_branches_compile_against_the_api_stub(cpp_bins):
+    """-DHPXFFT_B200_WITH_HPX against tests/cpp/hpx_stub (the subset of the HPX API the headers use; HPX itself is absent here):
+    vector_2d serialisation round trip and the HPX bootstrap calls.  CPU only."""
+    r = run([os.path.join(cpp_bins, "test_hpx_branch")])
+    assert r.returncode == 0 and "test_hpx_branch ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_hpx_branch_agas_futures(cpp_bins):
+    r = run([os.path.join(cpp_bins, "test_hpx_branch"), "gpu"], env={"RANK": "0", "WORLD_SIZE": "1"})
+    assert r.returncode == 0 and "test_hpx_branch ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_cpp_agas_clients(cpp_bins):
     r = run([os.path.join(cpp_bins, "test_agas")], env={"RANK": "0", "WORLD_SIZE": "1"})
