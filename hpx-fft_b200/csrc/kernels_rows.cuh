@@ -54,27 +54,6 @@ __device__ __forceinline__ void herm_pair(cd a, cd b, cd w, cd &xk, cd &xmk)
     xmk = make_double2(e.x - t.y, -(e.y + t.x));
 }
 
-// Long rows (m = M*C > 8192 complex): decimation in frequency over the leading index.  CTA c of a row
-// computes y_c[j] = w_m^(j c) * sum_{j1<C} z[j + j1 M] w_C^(j1 c), whose M-point FFT is Z[c + C k2].
-// Every CTA reads the whole row (served by L2 for all but the first reader) and no CTA talks to another.
-template <int M, int C>
-__device__ __forceinline__ cd load_split(const cd *__restrict__ zrow, int idx, int c, const cd *__restrict__ tw)
-{
-    if constexpr (C == 1) {
-        return ld_stream(zrow + idx);
-    } else if constexpr (C == 2) {
-        const cd a = ld_stream(zrow + idx), b = ld_stream(zrow + idx + M);
-        if (c == 0) return cadd(a, b);
-        return cmul(csub(a, b), ldtw(tw, 2u * (unsigned) idx));
-    } else {
-        cd acc = ld_stream(zrow + idx);
-#pragma unroll
-        for (int j1 = 1; j1 < C; ++j1)
-            acc = cadd(acc, cmul(ld_stream(zrow + idx + j1 * M), ldtw(tw, (unsigned) ((j1 * c) % C) * (unsigned) (2 * M))));
-        return c == 0 ? acc : cmul(acc, ldtw(tw, 2u * (unsigned) idx * (unsigned) c));
-    }
-}
-
 // cp.async (LDGSTS) 16-byte global -> shared copy, L2-only caching; used to stage the NEXT row's raw
 // input into the pencil buffer while the current row is still in its register-only tail
 // (last-pass butterflies, Hermitian split, stores)
@@ -83,20 +62,6 @@ __device__ __forceinline__ void cp_async16(cd *dst_smem, const cd *src_gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned) __cvta_generic_to_shared(dst_smem)), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// Long rows (C > 1) cannot be staged (the pencil buffer only holds 1/C of a row): instead every CTA of the row pulls
-// its 1/C of the NEXT row into L2 while the current row finishes in registers, so that the first pass's
-// streaming loads find the row in L2 instead of paying the HBM latency.
-template <int M, int C> __device__ __forceinline__ void prefetch_row_l2(const cd *__restrict__ zrow, int c)
-{
-    constexpr int LINES = M / 8; // 128-byte lines of this CTA's share
-    const cd *base = zrow + (size_t) c * M;
-#pragma unroll
-    for (int i = 0; i < (LINES + ROW_THREADS - 1) / ROW_THREADS; ++i) {
-        const int ln = i * ROW_THREADS + (int) threadIdx.x;
-        if (ln < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ln * 8));
-    }
-}
 
 template <int M> __device__ __forceinline__ void stage_row(cd *sm, const cd *__restrict__ zrow, int lt)
 {
@@ -110,13 +75,13 @@ template <int M> __device__ __forceinline__ void stage_row(cd *sm, const cd *__r
 //   tw2[r*JW + j]  = w_M^(r j)                last pass, r < 16, j <= PP/2 (column PP-j uses the conjugate:
 //                                             w_M^(r (PP-j)) = w_16^r conj(w_M^(r j)), and the w_16^r factor
 //                                             only rotates the butterfly's output index by one)
-//   tw3[j]         = w_n^(c + C j)            Hermitian split, j <= PP/2; the s-dependence is w_32^s, a constant
+//   tw3[j]         = w_n^j                    Hermitian split, j <= PP/2; the s-dependence is w_32^s, a constant
 template <int M> __host__ __device__ constexpr int row_jw() { return M / 32 + 1; }
 template <int M> __host__ __device__ constexpr int row_tw1_entries() { return RowPlan<M>::NPRE == 2 ? RowPlan<M>::R0 * RowPlan<M>::R1 : 0; }
 template <int M> __host__ __device__ constexpr int row_tw_entries() { return row_tw1_entries<M>() + 17 * row_jw<M>(); }
 template <int M> __host__ __device__ constexpr size_t row_smem_total() { return row_smem_bytes<M>() + (size_t) row_tw_entries<M>() * sizeof(cd); }
 
-// one prefix pass: radix R, NS = product of earlier radices
+// one prefix pass: radix R, NS = product of earlier radices (C, zrow, tw, c: unused, kept for the callers in the long-row kernels)
 template <int M, int C, int R, int NS, bool FIRST>
 __device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__restrict__ zrow, const cd *__restrict__ tw, const cd *tw1,
                                          int lt, int c)
@@ -129,12 +94,9 @@ __device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__re
         const int j = lt + b * TPR;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (FIRST) {
-                if constexpr (C == 1)
-                    v[b * R + r] = sm[j + r * T]; // raw row staged by cp.async (identity layout, thread-private)
-                else
-                    v[b * R + r] = load_split<M, C>(zrow, j + r * T, c, tw);
-            } else
+            if (FIRST)
+                v[b * R + r] = sm[j + r * T]; // raw row staged by cp.async (identity layout, thread-private)
+            else
                 v[b * R + r] = sm[rpad<PS>(j + r * T)];
         }
     }
@@ -158,23 +120,20 @@ __device__ __forceinline__ void row_pass(cd (&v)[ROW_PT], cd *sm, const cd *__re
     __syncthreads();
 }
 
-// tw: w_n^i, i < n = 2*M*C.  V rows have `pitch` complex (= cy) elements.  grid = (persistent CTAs, C).
-// C <= 2: Hermitian split fused (the partner of Z[c + C k2] lives in the same CTA); output via RowDst.
-// C  > 2: the partner lives in CTA C-c, so the raw Z is written to `zraw` (row-major, pitch m = M*C) and
-//         herm_split_kernel finishes the job.
-// FASTADDR: single destination rank and 16 | C*PP -- output pointers advance by a constant per s.
-template <int M, int C, bool FASTADDR>
+// tw: w_n^i, i < n = 2*M.  V rows have `pitch` complex (= cy) elements.  grid = persistent CTAs.
+// Rows longer than one pencil (ny >= 32768) are handled by kernels_rows_long2.cuh / kernels_rows_long.cuh.
+// FASTADDR: single destination rank and CW | PP -- output pointers advance by a constant per s.
+template <int M, bool FASTADDR>
 __global__ void __launch_bounds__(ROW_THREADS, 1)
-    rows_r2c_kernel(const cd *__restrict__ V, unsigned pitch, unsigned nxl, RowDst dst, const cd *__restrict__ tw, cd *__restrict__ zraw)
+    rows_r2c_kernel(const cd *__restrict__ V, unsigned pitch, unsigned nxl, RowDst dst, const cd *__restrict__ tw)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using P = RowPlan<M>;
     constexpr int PS = P::PS, TPR = row_tpr<M>(), G = row_group<M>(), LP = row_lp<M>();
     constexpr int PP = M / 16; // columns of the last pass
     constexpr int JW = row_jw<M>();
-    constexpr unsigned MM = (unsigned) M * C; // complex length of the whole row
+    constexpr unsigned MM = (unsigned) M; // complex length of the row
     const int g = threadIdx.x / TPR, lt = threadIdx.x % TPR;
-    const int c = C == 1 ? 0 : (int) blockIdx.y;
     cd *sm = reinterpret_cast<cd *>(smem_raw) + g * LP;
     cd *tw1 = reinterpret_cast<cd *>(smem_raw + row_smem_bytes<M>());
     cd *tw2 = tw1 + row_tw1_entries<M>();
@@ -185,16 +144,15 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
     if constexpr (P::NPRE == 2) {
         for (int i = threadIdx.x; i < P::R0 * P::R1; i += ROW_THREADS) {
             const int r = i / P::R0, k = i - r * P::R0;
-            tw1[i] = ldtw(tw, (unsigned) (r * k) * (unsigned) (2 * C * M / (P::R0 * P::R1)));
+            tw1[i] = ldtw(tw, (unsigned) (r * k) * (unsigned) (2 * M / (P::R0 * P::R1)));
         }
     }
     for (int i = threadIdx.x; i < 16 * JW; i += ROW_THREADS) {
         const int r = i / JW, j = i - r * JW;
-        tw2[i] = ldtw(tw, (unsigned) (2 * C) * (unsigned) (r * j));
+        tw2[i] = ldtw(tw, 2u * (unsigned) (r * j));
     }
-    for (int i = threadIdx.x; i < JW; i += ROW_THREADS) tw3[i] = ldtw(tw, (unsigned) c + (unsigned) C * (unsigned) i);
+    for (int i = threadIdx.x; i < JW; i += ROW_THREADS) tw3[i] = ldtw(tw, (unsigned) i);
 
-    const bool odd = (C == 2 && c == 1);
     auto row_ptr = [&](unsigned grp) -> const cd * {
         unsigned row = grp * G + g;
 #ifdef HPXFFT_B200_DIAG_WRAP
@@ -202,9 +160,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
 #endif
         return V + (unsigned long long) (row < nxl ? row : nxl - 1) * pitch;
     };
-    if constexpr (C == 1) {
-        if (blockIdx.x < ngroups) stage_row<M>(sm, row_ptr(blockIdx.x), lt);
-    }
+    if (blockIdx.x < ngroups) stage_row<M>(sm, row_ptr(blockIdx.x), lt);
     for (unsigned grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
 #ifdef HPXFFT_B200_DIAG_WRAP
         const unsigned row = (grp * G + g) & 63u;
@@ -214,38 +170,24 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
         const bool valid = row < nxl;
         const cd *zrow = row_ptr(grp);
         cd v[ROW_PT];
-        if constexpr (C == 1) cp_async_wait_all(); // own copies landed; each thread only reads what it staged itself
-        row_pass<M, C, P::R0, 1, true>(v, sm, zrow, tw, tw1, lt, c);
-        if constexpr (P::NPRE == 2) row_pass<M, C, P::R1, P::R0, false>(v, sm, zrow, tw, tw1, lt, c);
+        cp_async_wait_all(); // own copies landed; each thread only reads what it staged itself
+        row_pass<M, 1, P::R0, 1, true>(v, sm, zrow, tw, tw1, lt, 0);
+        if constexpr (P::NPRE == 2) row_pass<M, 1, P::R1, P::R0, false>(v, sm, zrow, tw, tw1, lt, 0);
 
-        // ---- last pass: two radix-16 butterflies (columns jA, jB) ----
-        // partner of k2 is M - k2 (c == 0) or M - 1 - k2 (C == 2, c == 1)
-        const int jA = lt, jB = odd ? PP - 1 - lt : (lt ? PP - lt : PP / 2);
+        // ---- last pass: two radix-16 butterflies (columns jA, jB); the partner of k2 is M - k2 ----
+        const int jA = lt, jB = lt ? PP - lt : PP / 2;
         cd A[16], B[16];
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             A[r] = sm[rpad<PS>(jA + r * PP)];
             B[r] = sm[rpad<PS>(jB + r * PP)];
         }
-        if constexpr (C == 1) {
-            // the pencil buffer is dead until the next row's first pass: refill it with the next row's
-            // raw input while this row finishes in registers
-            __syncthreads();
-            if (grp + gridDim.x < ngroups) stage_row<M>(sm, row_ptr(grp + gridDim.x), lt);
-        }
-#ifndef HPXFFT_B200_NO_ROW_PREFETCH
-        else if (grp + gridDim.x < ngroups)
-            prefetch_row_l2<M, C>(row_ptr(grp + gridDim.x), c);
-#endif
-        // rotated == column jB got conj twiddles, its natural output s sits at butterfly output (s+1)&15
-        const bool rotated = odd || lt != 0;
-        if (odd) {
-#pragma unroll
-            for (int r = 1; r < 16; ++r) {
-                A[r] = cmul(A[r], tw2[r * JW + jA]);
-                B[r] = cmulc(B[r], tw2[r * JW + jA + 1]); // jB = PP - (jA + 1)
-            }
-        } else if (lt != 0) {
+        // the pencil buffer is dead until the next row's first pass: refill it with the next row's
+        // raw input while this row finishes in registers
+        __syncthreads();
+        if (grp + gridDim.x < ngroups) stage_row<M>(sm, row_ptr(grp + gridDim.x), lt);
+        // column jB gets conj twiddles (w_M^(r (PP - j)) = w_16^r conj(w_M^(r j))): its natural output s sits at butterfly output (s+1)&15
+        if (lt != 0) {
 #pragma unroll
             for (int r = 1; r < 16; ++r) {
                 const cd t = tw2[r * JW + jA];
@@ -258,38 +200,16 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
         }
         fft_dif<16>(A);
         fft_dif<16>(B);
-        // natural order: Z[c + C*(jA + s*PP)] = A[bitrev(s)],  Z[c + C*(jB + s*PP)] = B[bitrev(rotated ? s+1 : s)]
-        if constexpr (C > 2) {
-            if (valid) {
-                cd *zr = zraw + (unsigned long long) row * MM;
-#pragma unroll
-                for (int s = 0; s < 16; ++s) st_stream(zr + (unsigned) c + (unsigned) C * (unsigned) (jA + s * PP), A[bitrev(s, 4)]);
-                if (rotated) {
-#pragma unroll
-                    for (int s = 0; s < 16; ++s)
-                        st_stream(zr + (unsigned) c + (unsigned) C * (unsigned) (jB + s * PP), B[bitrev((s + 1) & 15, 4)]);
-                } else {
-#pragma unroll
-                    for (int s = 0; s < 16; ++s) st_stream(zr + (unsigned) c + (unsigned) C * (unsigned) (jB + s * PP), B[bitrev(s, 4)]);
-                }
-            }
-        } else if (rotated) {
-            const cd wb = tw3[jA]; // w_n^(c + C jA)
+        // natural order: Z[jA + s*PP] = A[bitrev(s)],  Z[jB + s*PP] = B[bitrev(lt ? s+1 : s)]
+        if (lt != 0) {
+            const cd wb = tw3[jA]; // w_n^jA
             cd *pk = nullptr, *pm = nullptr;
             long long step = 0;
             if constexpr (FASTADDR) {
-#ifdef HPXFFT_B200_DIAG_CONTIG_STORE
-                const unsigned k0 = (unsigned) c * (unsigned) M + (unsigned) jA, m0 = MM - k0;
-#else
-                const unsigned k0 = (unsigned) c + (unsigned) C * (unsigned) jA, m0 = MM - k0;
-#endif
+                const unsigned k0 = (unsigned) jA, m0 = MM - k0;
                 pk = dst.base[0] + (unsigned long long) (k0 >> CW_SHIFT) * dst.tile_stride + (unsigned long long) row * CW + (k0 & (unsigned) (CW - 1));
                 pm = dst.base[0] + (unsigned long long) (m0 >> CW_SHIFT) * dst.tile_stride + (unsigned long long) row * CW + (m0 & (unsigned) (CW - 1));
-#ifdef HPXFFT_B200_DIAG_CONTIG_STORE
                 step = (long long) (PP >> CW_SHIFT) * (long long) dst.tile_stride;
-#else
-                step = (long long) ((C * PP) >> CW_SHIFT) * (long long) dst.tile_stride;
-#endif
             }
 #pragma unroll
             for (int s = 0; s < 16; ++s) {
@@ -301,14 +221,14 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
                         st_stream(pk + s * step, xk);
                         st_stream(pm - s * step, xmk);
                     } else {
-                        const unsigned kA = (unsigned) c + (unsigned) C * (unsigned) (jA + s * PP);
+                        const unsigned kA = (unsigned) (jA + s * PP);
                         st_stream(rowdst_ptr(dst, row, kA), xk);
                         st_stream(rowdst_ptr(dst, row, MM - kA), xmk);
                     }
                 }
             }
         } else {
-            // lt == 0, c == 0: columns 0 and PP/2 are their own partners
+            // lt == 0: columns 0 and PP/2 are their own partners
             const cd z0 = A[0];
             if (valid) {
                 st_stream(rowdst_ptr(dst, row, 0u), make_double2(z0.x + z0.y, 0.0));
@@ -316,7 +236,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
             }
 #pragma unroll
             for (int s = 1; s < 8; ++s) {
-                const unsigned k = (unsigned) C * (unsigned) (s * PP);
+                const unsigned k = (unsigned) (s * PP);
                 cd xk, xmk;
                 herm_pair(A[bitrev(s, 4)], A[bitrev(16 - s, 4)], mulw32(make_double2(1.0, 0.0), s), xk, xmk);
                 if (valid) {
@@ -324,11 +244,11 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
                     st_stream(rowdst_ptr(dst, row, MM - k), xmk);
                 }
             }
-            if (valid) st_stream(rowdst_ptr(dst, row, (unsigned) C * (unsigned) (8 * PP)), cconj(A[bitrev(8, 4)]));
-            const cd wh = tw3[PP / 2]; // w_n^(C PP/2)
+            if (valid) st_stream(rowdst_ptr(dst, row, (unsigned) (8 * PP)), cconj(A[bitrev(8, 4)]));
+            const cd wh = tw3[PP / 2]; // w_n^(PP/2)
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
-                const unsigned k = (unsigned) C * (unsigned) (PP / 2 + s * PP);
+                const unsigned k = (unsigned) (PP / 2 + s * PP);
                 cd xk, xmk;
                 herm_pair(B[bitrev(s, 4)], B[bitrev(15 - s, 4)], mulw32(wh, s), xk, xmk);
                 if (valid) {
@@ -337,28 +257,6 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
                 }
             }
         }
-    }
-}
-
-// Hermitian split as a separate pass (rows longer than 2*8192 complex): zraw[row][k], k < m  ->  X[k], k <= m.
-// grid = (nxl, ceil((m/2+1)/256))  -- rows on grid.x: a slab may have more than 65535 rows
-static __global__ void herm_split_kernel(const cd *__restrict__ zraw, unsigned m, unsigned nxl, RowDst dst, const cd *__restrict__ tw)
-{
-    const unsigned row = blockIdx.x;
-    const unsigned k = blockIdx.y * blockDim.x + threadIdx.x;
-    if (row >= nxl || k > m / 2) return;
-    const cd *zr = zraw + (unsigned long long) row * m;
-    if (k == 0) {
-        const cd z0 = zr[0];
-        *rowdst_ptr(dst, row, 0u) = make_double2(z0.x + z0.y, 0.0);
-        *rowdst_ptr(dst, row, m) = make_double2(z0.x - z0.y, 0.0);
-    } else if (2 * k == m) {
-        *rowdst_ptr(dst, row, k) = cconj(zr[k]);
-    } else {
-        cd xk, xmk;
-        herm_pair(zr[k], zr[m - k], ldtw(tw, k), xk, xmk);
-        *rowdst_ptr(dst, row, k) = xk;
-        *rowdst_ptr(dst, row, m - k) = xmk;
     }
 }
 

@@ -13,7 +13,7 @@
 // What this replaces (round 1): C CTAs per row, each re-reading the row from HBM and storing the bins k = c (mod C)
 // it owned as isolated 16-byte elements.  ncu on 32768^2: 34.5 GB read + 17.0 GB written for 8.6 + 8.6 GB of
 // algorithmic traffic (two HBM reads of every row, a read-modify-write fill for every half-written sector); for C > 2
-// additionally a full HBM round trip through a raw-spectrum buffer and herm_split_kernel.
+// additionally a full HBM round trip through a raw-spectrum buffer and a separate Hermitian-split kernel.
 #pragma once
 #include "kernels_rows.cuh"
 

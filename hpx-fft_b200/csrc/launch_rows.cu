@@ -10,33 +10,27 @@ namespace hpxfft_b200 {
 
 namespace {
 
-template <int M, int C, bool FAST> int launch_rows_big_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+template <int M, bool FAST> int launch_rows_big_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
 {
     constexpr size_t smem = row_smem_total<M>();
-    if (int rc = ensure_smem(rows_r2c_kernel<M, C, FAST>, smem, p->device)) return rc;
+    if (int rc = ensure_smem(rows_r2c_kernel<M, FAST>, smem, p->device)) return rc;
     const unsigned ngroups = (nrows + row_group<M>() - 1) / row_group<M>();
     // one resident CTA per SM (shared memory bound): persistent CTAs amortise the twiddle-table build
     const int sms = p->sm_count - p->sm_reserve;
-    const unsigned cap = (unsigned) sms / C > 0 ? (unsigned) sms / C : 1u;
+    const unsigned cap = sms > 0 ? (unsigned) sms : 1u;
     const unsigned grid = ngroups < cap ? ngroups : cap;
-    if (C > 2 && !p->zraw) return fail(HPXFFT_B200_ESTATE, "long-row scratch missing");
-    rows_r2c_kernel<M, C, FAST><<<dim3(grid, C), ROW_THREADS, smem, p->stream>>>(V, pitch, nrows, dst, p->tw_row, p->zraw);
+    rows_r2c_kernel<M, FAST><<<grid, ROW_THREADS, smem, p->stream>>>(V, pitch, nrows, dst, p->tw_row);
     CU(cudaGetLastError());
-    if (C > 2) {
-        const unsigned m = (unsigned) M * C;
-        herm_split_kernel<<<dim3(nrows, (m / 2 + 1 + 255) / 256), 256, 0, p->stream>>>(p->zraw, m, nrows, dst, p->tw_row);
-        CU(cudaGetLastError());
-    }
     return 0;
 }
 
-template <int M, int C = 1> int launch_rows_big(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+template <int M> int launch_rows_big(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
 {
-    // fast output addressing: one destination rank and tile-aligned per-s stride (the 1-GPU hot configs)
-    if constexpr (M == 8192 && C <= 2) {
-        if (dst.P == 1) return launch_rows_big_t<M, C, true>(p, dst, nrows, V, pitch);
+    // fast output addressing: one destination rank and tile-aligned per-s stride (the 1-GPU hot config)
+    if constexpr (M == 8192) {
+        if (dst.P == 1) return launch_rows_big_t<M, true>(p, dst, nrows, V, pitch);
     }
-    return launch_rows_big_t<M, C, false>(p, dst, nrows, V, pitch);
+    return launch_rows_big_t<M, false>(p, dst, nrows, V, pitch);
 }
 
 // rows longer than one pencil: one persistent CTA per row, C sequential sub-FFTs, L2-resident scratch (kernels_rows_long.cuh)
@@ -75,31 +69,17 @@ template <bool FAST> int launch_rows_long2_t(const hpxfft_b200_plan *p, const Ro
     return 0;
 }
 
+// read per launch (cheap) so that the parity tests can select the variants in one process
 int rows_long_variant()
 {
-    static const int v = [] {
-        const char *e = getenv("HPXFFT_B200_ROWS_LONG");
-        return e ? atoi(e) : 2;
-    }();
-    return v;
+    const char *e = getenv("HPXFFT_B200_ROWS_LONG");
+    return e ? atoi(e) : 2;
 }
 
 bool rows_v1_path()
 {
-    static const bool v = [] {
-        const char *e = getenv("HPXFFT_B200_ROWS_V1");
-        return e && e[0] == '1';
-    }();
-    return v;
-}
-
-bool rows_old_path()
-{
-    static const bool v = [] {
-        const char *e = getenv("HPXFFT_B200_ROWS_OLD");
-        return e && e[0] == '1';
-    }();
-    return v;
+    const char *e = getenv("HPXFFT_B200_ROWS_V1");
+    return e && e[0] == '1';
 }
 
 template <int M> int launch_rows_tiny(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
@@ -112,7 +92,7 @@ template <int M> int launch_rows_tiny(const hpxfft_b200_plan *p, const RowDst &d
 
 }  // namespace
 
-int rows_launch_count(size_t m) { return (m > 16384 && rows_old_path()) ? 2 : 1; }
+int rows_launch_count(size_t) { return 1; }
 
 int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m)
 {
@@ -136,11 +116,10 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
         if (rows_v1_path()) return launch_rows_big<8192>(p, dst, nrows, V, pitch);
         return dst.P == 1 ? launch_rows_v2_t<true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false>(p, dst, nrows, V, pitch);
     case 16384:
-        if (rows_old_path()) return launch_rows_big<8192, 2>(p, dst, nrows, V, pitch);
         if (rows_long_variant() != 2) return launch_rows_long<2>(p, dst, nrows, V, pitch); // HPXFFT_B200_ROWS_LONG=1: generic long-row kernel
         return dst.P == 1 ? launch_rows_long2_t<true>(p, dst, nrows, V, pitch) : launch_rows_long2_t<false>(p, dst, nrows, V, pitch);
-    case 32768: return rows_old_path() ? launch_rows_big<8192, 4>(p, dst, nrows, V, pitch) : launch_rows_long<4>(p, dst, nrows, V, pitch);
-    case 65536: return rows_old_path() ? launch_rows_big<8192, 8>(p, dst, nrows, V, pitch) : launch_rows_long<8>(p, dst, nrows, V, pitch);
+    case 32768: return launch_rows_long<4>(p, dst, nrows, V, pitch);
+    case 65536: return launch_rows_long<8>(p, dst, nrows, V, pitch);
     default: return fail(HPXFFT_B200_EINVAL, "unsupported row length ny=%zu (ny/2 must be a power of two <= 65536)", 2 * m);
     }
 }

@@ -946,13 +946,8 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     }
     CUB(cudaMalloc(&p->V, bytesV));
     CUB(cudaMalloc(&p->bufB, p->bytesB));
-    if (!p->rows_generic && p->m > 8192) {
-        // long rows: per-CTA raw-spectrum scratch of the row kernel (L2-resident); HPXFFT_B200_ROWS_OLD=1 (round-1 kernels, A/B
-        // runs only) needs the full-size raw buffer instead
-        const char *e = getenv("HPXFFT_B200_ROWS_OLD");
-        const size_t rows = (e && e[0] == '1') ? p->nxl : (size_t) p->sm_count;
-        CUB(cudaMalloc(&p->zraw, rows * p->m * sizeof(cd)));
-    }
+    if (is_pow2(p->m) && p->m > 8192) // long rows: per-CTA scratch of the row kernel (one CTA per SM, rewritten per row, L2-resident)
+        CUB(cudaMalloc(&p->zraw, (size_t) p->sm_count * p->m * sizeof(cd)));
     if (p->bytesS) CUB(cudaMalloc(&p->S, p->bytesS));
     if (p->fused) CUB(cudaMalloc(&p->ctl, (1 + 2 * (size_t) p->ntiles * p->col_split) * sizeof(unsigned)));
     if (p->bytesA) CUB(cudaMalloc(&p->bufA, p->bytesA));
@@ -1383,10 +1378,7 @@ int hpxfft_b200_r2c_rows(double *host_rows, size_t batch, size_t n_col, int devi
     CUR(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CUR(cudaMalloc(&p->V, bytes));
     CUR(cudaMalloc(&p->bufB, tbytes));
-    if (m > 8192) {
-        const char *e = getenv("HPXFFT_B200_ROWS_OLD");
-        CUR(cudaMalloc(&p->zraw, ((e && e[0] == '1') ? batch : (size_t) p->sm_count) * m * sizeof(cd)));
-    }
+    if (m > 8192) CUR(cudaMalloc(&p->zraw, (size_t) p->sm_count * m * sizeof(cd)));
     CUR(cudaMalloc(&p->tw_row, t.size() * sizeof(double2)));
     CUR(cudaMemcpyAsync(p->tw_row, t.data(), t.size() * sizeof(double2), cudaMemcpyHostToDevice, p->stream));
     CUR(cudaMemcpyAsync(p->V, host_rows, bytes, cudaMemcpyHostToDevice, p->stream));

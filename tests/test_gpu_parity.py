@@ -78,6 +78,23 @@ def test_r2c_rows(pkg, lib, oracle, ny):
     assert oracle.rel_l2(got, np.ascontiguousarray(ref).view(np.longdouble).reshape(batch, -1)) <= 1e-13
 
 
+@pytest.mark.parametrize("env,ny", [({"HPXFFT_B200_ROWS_V1": "1"}, 16384), ({"HPXFFT_B200_ROWS_LONG": "1"}, 32768)])
+def test_r2c_rows_selectable_variants(pkg, lib, oracle, monkeypatch, env, ny):
+    """The row kernels that are not the default for their length stay selectable for A/B runs and stay correct:
+    ROWS_V1: the Stockham kernel rows_r2c_kernel<8192> for ny = 16384 (default: rows_r2c_v2_kernel);
+    ROWS_LONG=1: the generic long-row kernel rows_long_kernel<2> for ny = 32768 (default: rows_long2_kernel)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    batch = 5
+    a = np.zeros((batch, ny + 2))
+    a[:, :ny] = np.random.default_rng(ny + 1).uniform(-1, 1, (batch, ny))
+    got = a.copy()
+    pkg.capi.check(lib.hpxfft_b200_r2c_rows(got.ctypes.data, batch, ny + 2, 0))
+    import scipy.fft as sfft
+    ref = sfft.rfft(a[:, :ny].astype(np.longdouble), axis=1)
+    assert oracle.rel_l2(got, np.ascontiguousarray(ref).view(np.longdouble).reshape(batch, -1)) <= 1e-13
+
+
 # variant 0 = what a plan launches: the persistent fused four-step kernel for n > 256, i.e. every (N1, N2) pair of
 # launch_fused.cu -- 512 (32,16), 1024 (32,32), 2048 (64,32), 4096 (64,64), 8192 (128,64), 16384 (128,128),
 # 32768 (256,128), 65536 (256,256), 131072 (512,256), 262144 (512,512); variant 1 = the unfused launches.
