@@ -35,6 +35,7 @@ enum Transport {
 };
 
 inline bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
+struct BlueStage;
 
 template <class K> int set_smem(K kernel, size_t bytes)
 {
@@ -60,6 +61,8 @@ struct hpxfft_b200_plan {
     unsigned gen_ct = 1, gen_cq = 0;                 // column length nx = gen_ct * gen_cq
     hpxfft_b200::cd *S1 = nullptr;                   // output of the odd-radix column pre-stage
     hpxfft_b200_plan *colsub = nullptr;              // plan-view of the power-of-two column stage (length gen_cq, reads S1)
+    bool rows_blue = false, cols_blue = false;       // ... any other length above the direct-DFT bound: Bluestein (kernels_bluestein.cuh)
+    hpxfft_b200::BlueStage *blue_r = nullptr, *blue_c = nullptr;
     // device buffers
     double *V = nullptr;              // slab, nxl x n_col doubles
     hpxfft_b200::cd *bufA = nullptr;  // send staging of exchange #1 and #2 (TR_NCCL, TR_CE)
@@ -123,10 +126,19 @@ int launch_cols_generic(const hpxfft_b200_plan *p, const InterView &in, const Co
 void gen_factor(size_t n, unsigned &t, unsigned &q, unsigned &lg);
 bool gen_rows_supported(size_t m);
 bool gen_cols_supported(size_t nx);
+int make_col_stage(const hpxfft_b200_plan *parent, unsigned q, unsigned nstrips, hpxfft_b200_plan **out);
+void free_col_stage(hpxfft_b200_plan *s);
+int run_col_stage(const hpxfft_b200_plan *s, const InterView &iv, const ColDst &out, unsigned nstrips, int *launches);
 int gen_setup_col_stage(hpxfft_b200_plan *p);
 void gen_free_col_stage(hpxfft_b200_plan *p);
 int launch_rows_mixed(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m);
 int launch_cols_mixed(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, int *launches);
+// Bluestein (launch_bluestein.cu): any length, on top of the power-of-two column stage
+struct BlueStage;
+int blue_setup(hpxfft_b200_plan *p, bool rows, size_t n, unsigned max_strips);
+void blue_free(hpxfft_b200_plan *p);
+int launch_rows_blue(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch);
+int launch_cols_blue(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, int *launches);
 
 // exp(-2 pi i k / n), k < n, rounded from long double; exact on the axes and diagonals
 void make_twiddles(std::vector<double2> &t, size_t n);

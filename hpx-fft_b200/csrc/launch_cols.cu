@@ -57,6 +57,10 @@ int launch_cols(const hpxfft_b200_plan *p, const InterView &in, const ColDst &ou
         if (mid) CU(cudaEventRecord(mid, p->stream));
         return launch_cols_mixed(p, in, out, launches);
     }
+    if (p->cols_blue) {
+        if (mid) CU(cudaEventRecord(mid, p->stream));
+        return launch_cols_blue(p, in, out, launches);
+    }
     if (p->cols_generic) {
         if (launches) *launches += 1;
         if (mid) CU(cudaEventRecord(mid, p->stream));

@@ -60,23 +60,20 @@ int launch_rows_mixed(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nro
     return launch_rows_mixed_t<32, 256>(p, dst, nrows, V, pitch, a);
 }
 
-// plan-view of the power-of-two stage: a column FFT of length q over (strips * t) virtual strips that reads S1
-int gen_setup_col_stage(hpxfft_b200_plan *p)
+// plan-view of a power-of-two column stage: a column FFT of length q (= 2^lg) over `nstrips` strips, with its own twiddle tables,
+// scratch ring and counters; shares the parent's device and stream
+int make_col_stage(const hpxfft_b200_plan *parent, unsigned q, unsigned nstrips, hpxfft_b200_plan **out)
 {
-    unsigned t, q, lg;
-    gen_factor(p->nx, t, q, lg);
-    p->gen_ct = t;
-    p->gen_cq = q;
-    CU(cudaMalloc(&p->S1, (size_t) p->ntiles * p->nx * CW * sizeof(cd)));
-    if (q == 1) return 0;
+    unsigned lg = 0;
+    while ((1u << lg) < q) ++lg;
     hpxfft_b200_plan *s = new hpxfft_b200_plan();
-    p->colsub = s;
-    s->device = p->device;
-    s->sm_count = p->sm_count;
-    s->stream = p->stream; // shared, not owned
+    *out = s;
+    s->device = parent->device;
+    s->sm_count = parent->sm_count;
+    s->stream = parent->stream; // shared, not owned
     s->nx = s->nxl = q;
-    s->ntiles = p->ntiles * t;
-    s->w = p->w;
+    s->ntiles = nstrips;
+    s->w = nstrips * CW;
     // same decomposition rules as the main plan (plan.cu: choose_col_split)
     if (q <= 256) {
         s->two_level = false;
@@ -116,19 +113,44 @@ int gen_setup_col_stage(hpxfft_b200_plan *p)
     return 0;
 }
 
+void free_col_stage(hpxfft_b200_plan *s)
+{
+    if (!s) return;
+    cudaFree(s->tw_col);
+    cudaFree(s->tw_il);
+    cudaFree(s->S);
+    cudaFree(s->ctl);
+    s->stream = nullptr;
+    delete s;
+}
+
+// runs the stage on the first `nstrips` strips of `iv` (fused persistent kernel when the pair exists)
+int run_col_stage(const hpxfft_b200_plan *s, const InterView &iv, const ColDst &out, unsigned nstrips, int *launches)
+{
+    if (s->fused) {
+        if (launches) *launches += 1;
+        return launch_cols_fused(s, iv, out, 0u, nstrips);
+    }
+    return launch_cols(s, iv, out, nstrips, s->S, (unsigned) s->nx, s->n1, s->n2, s->two_level, launches, nullptr);
+}
+
+int gen_setup_col_stage(hpxfft_b200_plan *p)
+{
+    unsigned t, q, lg;
+    gen_factor(p->nx, t, q, lg);
+    p->gen_ct = t;
+    p->gen_cq = q;
+    CU(cudaMalloc(&p->S1, (size_t) p->ntiles * p->nx * CW * sizeof(cd)));
+    if (q == 1) return 0;
+    return make_col_stage(p, q, p->ntiles * t, &p->colsub);
+}
+
 void gen_free_col_stage(hpxfft_b200_plan *p)
 {
     cudaFree(p->S1);
     p->S1 = nullptr;
-    if (hpxfft_b200_plan *s = p->colsub) {
-        cudaFree(s->tw_col);
-        cudaFree(s->tw_il);
-        cudaFree(s->S);
-        cudaFree(s->ctl);
-        s->stream = nullptr;
-        delete s;
-        p->colsub = nullptr;
-    }
+    free_col_stage(p->colsub);
+    p->colsub = nullptr;
 }
 
 int launch_cols_mixed(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, int *launches)
@@ -158,11 +180,7 @@ int launch_cols_mixed(const hpxfft_b200_plan *p, const InterView &in, const ColD
     iv.rank_stride = 0;
     ColDst o2 = out;
     o2.vt = a.t;
-    if (s->fused) {
-        if (launches) *launches += 1;
-        return launch_cols_fused(s, iv, o2, 0u, s->ntiles);
-    }
-    return launch_cols(s, iv, o2, s->ntiles, s->S, a.q, s->n1, s->n2, s->two_level, launches, nullptr);
+    return run_col_stage(s, iv, o2, s->ntiles, launches);
 }
 
 }  // namespace hpxfft_b200

@@ -97,6 +97,7 @@ int rows_launch_count(size_t) { return 1; }
 int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m)
 {
     if (p->rows_mixed) return launch_rows_mixed(p, dst, nrows, V, pitch, m);
+    if (p->rows_blue) return launch_rows_blue(p, dst, nrows, V, pitch);
     if (p->rows_generic) return launch_rows_generic(p, dst, nrows, V, pitch, m);
     switch (m) {
     case 1: return launch_rows_tiny<1>(p, dst, nrows, V, pitch);

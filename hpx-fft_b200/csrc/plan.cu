@@ -758,6 +758,7 @@ void hpxfft_b200_destroy(hpxfft_b200_plan *p)
         cudaStreamDestroy(p->cstream);
     }
     gen_free_col_stage(p);
+    blue_free(p);
     cudaFree(p->bufC);
     cudaFree(p->V);
     cudaFree(p->bufA);
@@ -840,21 +841,21 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     // runs 512 * t, t = 1..32); anything else falls back to the direct-DFT kernels, bounded to sizes where O(n^2) is sane
     constexpr size_t GENERIC_MAX = 8192;
     if (p->ny < 2) return bail(fail(HPXFFT_B200_EINVAL, "unsupported ny=%zu", p->ny));
+    constexpr size_t BLUE_MAX = 131072; // convolution length 2^18
     if (!is_pow2(p->m)) {
         p->rows_mixed = gen_rows_supported(p->m);
-        p->rows_generic = !p->rows_mixed;
+        p->rows_generic = !p->rows_mixed && p->ny <= GENERIC_MAX;
+        p->rows_blue = !p->rows_mixed && !p->rows_generic; // large prime factor: Bluestein over the half-length complex row
     }
     if (!is_pow2(p->nx)) {
         p->cols_mixed = gen_cols_supported(p->nx);
-        p->cols_generic = !p->cols_mixed;
+        p->cols_generic = !p->cols_mixed && p->nx <= GENERIC_MAX;
+        p->cols_blue = !p->cols_mixed && !p->cols_generic;
     }
-    if (p->rows_generic ? p->ny > GENERIC_MAX : (!p->rows_mixed && p->m > 65536))
-        return bail(fail(HPXFFT_B200_EINVAL,
-                         "unsupported ny=%zu: ny/2 must be a power of two <= 65536, or (odd factor < 32) * 2^a <= 8192, or ny <= %zu", p->ny,
-                         GENERIC_MAX));
-    if (p->cols_generic ? p->nx > GENERIC_MAX : (!p->cols_mixed && p->nx > (1u << 18)))
-        return bail(fail(HPXFFT_B200_EINVAL, "unsupported nx=%zu: must be a power of two <= 2^18, or (odd factor <= 127) * 2^a, or <= %zu", p->nx,
-                         GENERIC_MAX));
+    if ((is_pow2(p->m) && p->m > 65536) || (p->rows_blue && p->m > BLUE_MAX))
+        return bail(fail(HPXFFT_B200_EINVAL, "unsupported ny=%zu: ny/2 must be a power of two <= 65536 or any other length <= %zu", p->ny, BLUE_MAX));
+    if ((is_pow2(p->nx) && p->nx > (1u << 18)) || (p->cols_blue && p->nx > BLUE_MAX))
+        return bail(fail(HPXFFT_B200_EINVAL, "unsupported nx=%zu: must be a power of two <= 2^18 or any other length <= %zu", p->nx, BLUE_MAX));
     if (p->cy < (size_t) nranks) return bail(fail(HPXFFT_B200_EINVAL, "ny/2+1=%zu columns cannot be split over %d localities", p->cy, nranks));
 
     // column ownership: c_q = q*floor(cy/P), the last rank absorbs cy mod P
@@ -871,7 +872,7 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     p->c0 = p->c0_of[rank];
     p->ntiles = p->ntiles_of[rank];
     choose_col_split(p->nx, p->n1, p->n2, p->two_level, &p->col_split);
-    if (p->cols_generic || p->cols_mixed) {
+    if (p->cols_generic || p->cols_mixed || p->cols_blue) {
         p->two_level = false;
         p->n1 = (unsigned) p->nx;
         p->n2 = 1;
@@ -977,6 +978,10 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
 
     if (p->cols_mixed)
         if (int rc = gen_setup_col_stage(p)) return bail(rc);
+    if (p->rows_blue)
+        if (int rc = blue_setup(p, true, p->m, (unsigned) ((p->nxl + CW - 1) / CW))) return bail(rc);
+    if (p->cols_blue)
+        if (int rc = blue_setup(p, false, p->nx, p->ntiles)) return bail(rc);
 
     // sub-slab chunks (rank-invariant: derived from quantities every rank computes identically)
     if (p->transport == TR_CE || nccl_pipelined) {
@@ -1048,7 +1053,10 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
                  p->ny, t, q, t, t);
         p->row_desc = buf;
     }
-    if (p->cols_mixed)
+    if (p->rows_blue) p->row_desc = "r2c rows: Bluestein chirp-z over the half-length complex row (two power-of-two transforms on 16-row tiles), Hermitian split";
+    if (p->cols_blue)
+        snprintf(buf, sizeof(buf), "c2c columns: n=%zu Bluestein chirp-z (two power-of-two column transforms of the padded convolution length)", p->nx);
+    else if (p->cols_mixed)
         snprintf(buf, sizeof(buf), "c2c columns: n=%zu mixed radix %u x %u (odd-radix direct DFT pre-stage, then the power-of-two column kernels on %u virtual strips per strip)",
                  p->nx, p->gen_ct, p->gen_cq, p->gen_ct);
     else if (p->cols_generic)

@@ -87,3 +87,13 @@ def test_column_prestage_split2():                             # kernels_cols.cu
     rng = np.random.default_rng(3)
     y = rng.standard_normal(512) + 1j * rng.standard_normal(512)
     assert np.abs(mk.cols_split2_model(y, 16, 16) - np.fft.fft(y)).max() < 1e-10
+
+
+@pytest.mark.parametrize("n", [7, 97, 1021, 8209])
+def test_bluestein_chirp_z(n):                                 # kernels_bluestein.cuh
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    assert np.abs(mk.bluestein_model(x) - np.fft.fft(x)).max() < 1e-10 * np.sqrt(n)
+    z = rng.standard_normal(2 * n)                             # r2c of an even length 2n through the half-length complex transform
+    zc = z[0::2] + 1j * z[1::2]
+    assert np.abs(mk.herm_split(mk.bluestein_model(zc), 2 * n) - np.fft.rfft(z)).max() < 1e-10 * np.sqrt(n)

@@ -250,3 +250,22 @@ def cols_split2_model(y, n1, n2):
         yc = (y[:h] + y[h:]) if c2 == 0 else (y[:h] - y[h:]) * np.array([w(nx, x) for x in range(h)])
         out[c2 + 2 * np.arange(h)] = np.fft.fft(yc)
     return out
+
+
+def bluestein_model(x):
+    """kernels_bluestein.cuh / launch_bluestein.cu: X = c .* IFFT_M(FFT_M(x .* c, padded) .* FFT_M(h)), c[j] = exp(-i pi j^2/n),
+    h[l] = conj(c[|l|]) wrapped to length M = 2^p >= 2n-1; the inverse transform as conj(FFT(conj(.)))/M."""
+    n = len(x)
+    M = 1
+    while M < 2 * n - 1:
+        M <<= 1
+    j = np.arange(n)
+    c = np.exp(-1j * np.pi * ((j * j) % (2 * n)) / n)
+    h = np.zeros(M, complex)
+    h[:n] = np.conj(c)
+    h[M - np.arange(1, n)] = np.conj(c[1:])
+    a = np.zeros(M, complex)
+    a[:n] = x * c
+    P = np.fft.fft(a) * np.fft.fft(h)
+    p = np.conj(np.fft.fft(np.conj(P))) / M
+    return c * p[:n]
