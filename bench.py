@@ -186,6 +186,10 @@ def run_ours(args) -> dict | None:
         raise RuntimeError("bench.py: no CUDA device; hpxfft_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     # host staging buffers (e2e leg) live on the NUMA node of this rank's GPU
+    try:
+        orig_affinity = os.sched_getaffinity(0)
+    except Exception:
+        orig_affinity = None
     numa_bound = lib.hpxfft_b200_bind_host_to_device(local) == 0
 
     nx, ny = workload(args, world)
@@ -419,6 +423,11 @@ def run_ours(args) -> dict | None:
         if anchor:
             result["anchor_n1"] = anchor
         if world == 1 and not args.no_cpu_baseline:
+            if orig_affinity is not None:   # the CPU leg uses ALL host cores, not only those of the GPU's NUMA node
+                try:
+                    os.sched_setaffinity(0, orig_affinity)
+                except Exception:
+                    pass
             result["cpu_baseline"] = cpu_baseline(nx, ny, budget_s=args.cpu_budget)
     lib.hpxfft_b200_destroy(plan)
     if dist is not None:

@@ -127,7 +127,11 @@ __device__ __forceinline__ cd ld_stream(const cd *p)
 }
 __device__ __forceinline__ void st_stream(cd *p, cd v)
 {
+#ifdef HPXFFT_B200_DIAG_STORE_CG
+    asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory"); // diagnostic: normal L2 eviction priority
+#else
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+#endif
 }
 // L2-only (bypass L1) accesses for data produced by other CTAs of the same launch
 __device__ __forceinline__ cd ld_cg(const cd *p)
