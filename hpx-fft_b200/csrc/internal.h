@@ -70,8 +70,7 @@ struct hpxfft_b200_plan {
     hpxfft_b200::cd *zraw = nullptr;  // un-split row spectra, only for rows longer than 32768 reals
     hpxfft_b200::cd *S = nullptr;     // four-step scratch (full array, or an L2-resident ring of strips when fused)
     bool fused = false;               // level A + level B in one persistent launch
-    unsigned lag = 0, nslot = 0, fused_grid = 0; // lag / ring slots of the fused kernel, counted in super-groups of col_sg strips
-    unsigned col_sg = 1;              // strips per super-group of the fused column kernel (adjacent strips scheduled together)
+    unsigned lag = 0, nslot = 0, fused_grid = 0;
     unsigned *ctl = nullptr;          // tile counter + per-strip completion counters
     hpxfft_b200::cd *tw_row = nullptr, *tw_col = nullptr;
     hpxfft_b200::cd *tw_il = nullptr; // inter-level twiddles of the four-step column FFT, [x2][k1] = w_nx^(k1*x2)

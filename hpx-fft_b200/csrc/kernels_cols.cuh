@@ -233,7 +233,6 @@ struct FusedCtl {
     unsigned lag, nslot;
     unsigned discard; // level-B tiles discard their scratch lines from L2 after reading them
     unsigned ct0;     // first strip of this launch (chunked column pass); counters / ring slots are launch-local
-    unsigned sg;      // strips per super-group: tiles of `sg` adjacent strips are claimed interleaved (lag / nslot / counters count super-groups)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
@@ -307,15 +306,9 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
     cd *wil = ptw2 + col_tw_entries(N2);
     cd *wsp = wil + N1; // SPLIT == 2 only
     __shared__ unsigned s_tile;
-    // Super-groups: `sg` adjacent strips are scheduled together -- group G holds the level-A tiles of strips G*sg .. G*sg+sg-1
-    // (x2-major, strip-minor) followed by the level-B tiles of super-group G-lag (k1-major, strip-minor).  Consecutively claimed
-    // level-B tiles then write ADJACENT 256-byte pieces of the same output rows at about the same time (sg = 1: one strip at a time).
-    const unsigned SG = ctl.sg;
-    const unsigned PER_GROUP = SG * (unsigned) (N1 + N2), A_PART = SG * (unsigned) N2;
-    const unsigned ngroups = (ntiles + SG - 1) / SG;
-    const unsigned total = (ngroups + ctl.lag) * PER_GROUP;
+    constexpr unsigned PER_GROUP = N1 + N2;
+    const unsigned total = (ntiles + ctl.lag) * PER_GROUP;
     const unsigned long long slot_elems = (unsigned long long) N1 * N2 * CW;
-    auto strips_in = [&](unsigned G) -> unsigned { return ntiles - G * SG < SG ? ntiles - G * SG : SG; };
 
     fill_pass_twiddles<N1>(ptw1, tw, (unsigned) (SPLIT * N2), (int) threadIdx.x, NT);
     if (N1 != N2) fill_pass_twiddles<N2>(ptw2, tw, (unsigned) (SPLIT * N1), (int) threadIdx.x, NT);
@@ -328,13 +321,13 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
         target = 0;
         if (t >= total) return nullptr;
         const unsigned g = t / PER_GROUP, r = t - g * PER_GROUP;
-        if (r < A_PART) {
-            if (g >= ngroups || g < ctl.nslot) return nullptr;
-            target = (unsigned) N1 * strips_in(g - ctl.nslot);
+        if (r < (unsigned) N2) {
+            if (g >= ntiles || g < ctl.nslot) return nullptr;
+            target = (unsigned) N1;
             return ctl.doneB + (g - ctl.nslot);
         }
         if (g < ctl.lag) return nullptr;
-        target = (unsigned) N2 * strips_in(g - ctl.lag);
+        target = (unsigned) N2;
         return ctl.doneA + (g - ctl.lag);
     };
 
@@ -369,17 +362,16 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
         const unsigned g = t / PER_GROUP, r = t - g * PER_GROUP;
         unsigned *done = nullptr;
         bool synced = false; // did every thread pass a CTA barrier since it read s_tile?
-        if (r < A_PART) {
-            // level A: tile x2 of strip vs (virtual strip index inside this launch) in super-group g
-            const unsigned x2 = r / SG, sidx = r - x2 * SG, vs = g * SG + sidx;
-            if (g < ngroups && vs < ntiles) {
+        if (r < (unsigned) N2) {
+            // level A: tile x2 = r of strip g
+            if (g < ntiles) {
 #ifdef HPXFFT_B200_DIAG_WRAP
-                const unsigned ct = (ctl.ct0 + vs / SPLIT) & 1u;
+                const unsigned x2 = r, ct = (ctl.ct0 + g / SPLIT) & 1u;
 #else
-                const unsigned ct = ctl.ct0 + vs / SPLIT;
+                const unsigned x2 = r, ct = ctl.ct0 + g / SPLIT;
 #endif
                 for (int i = threadIdx.x; i < N1; i += NT) wil[i] = ldtw(W2, x2 * (unsigned) N1 + (unsigned) i);
-                cd *Sct = S + (unsigned long long) ((g % ctl.nslot) * SG + sidx) * slot_elems;
+                cd *Sct = S + (unsigned long long) (g % ctl.nslot) * slot_elems;
                 auto st = [&](int k1, int c, cd val) { st_cg(Sct + ((unsigned long long) k1 * N2 + x2) * CW + c, cmul(val, wil[k1])); };
                 if constexpr (SPLIT == 1) {
 #ifdef HPXFFT_B200_DIAG_NOLOAD_I
@@ -389,7 +381,7 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
 #endif
                     tile_fft<N1>(smem, ptw1, ld, st);
                 } else {
-                    const unsigned c2 = vs % SPLIT;
+                    const unsigned c2 = g % SPLIT;
                     const cd ws = ldtw(tw, x2); // w_nx^x2
                     // both halves of the column are read with default caching: the sibling virtual strip re-reads them from L2
                     auto ld = [&](int i, int c) -> cd {
@@ -402,16 +394,15 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
                 done = ctl.doneA + g;
                 synced = col_npass(N1) >= 2;
             }
-        } else if (g >= ctl.lag && (g - ctl.lag) * SG + (r - A_PART) % SG < ntiles) {
-            // level B: tile k1 of strip sl (virtual strip index inside this launch) in super-group gb = g - lag
-            const unsigned rb = r - A_PART, k1 = rb / SG, sidx = rb - k1 * SG, gb = g - ctl.lag, sl = gb * SG + sidx;
+        } else if (g >= ctl.lag) {
+            // level B: tile k1 = r - N2 of strip g - lag
 #ifdef HPXFFT_B200_DIAG_WRAP
-            const unsigned ct = (ctl.ct0 + sl / SPLIT) & 1u;
+            const unsigned k1 = r - N2, sl = g - ctl.lag, ct = (ctl.ct0 + sl / SPLIT) & 1u;
 #else
-            const unsigned ct = ctl.ct0 + sl / SPLIT;
+            const unsigned k1 = r - N2, sl = g - ctl.lag, ct = ctl.ct0 + sl / SPLIT;
 #endif
             const unsigned c2 = sl % SPLIT;
-            const cd *Sk = S + (unsigned long long) ((gb % ctl.nslot) * SG + sidx) * slot_elems + (unsigned long long) k1 * N2 * CW;
+            const cd *Sk = S + (unsigned long long) (sl % ctl.nslot) * slot_elems + (unsigned long long) k1 * N2 * CW;
             auto ld = [&](int i, int c) -> cd { return ld_cg(Sk + (unsigned) i * CW + c); };
             unsigned ctr, row0;
             coldst_strip(out, ct, ctr, row0);
@@ -435,7 +426,7 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
                 for (int ln = threadIdx.x; ln < N2 * CW * (int) sizeof(cd) / 128; ln += NT)
                     l2_discard_line(reinterpret_cast<const char *>(Sk) + (size_t) ln * 128);
             }
-            done = ctl.doneB + gb;
+            done = ctl.doneB + sl;
         }
         if (!synced) __syncthreads(); // skipped / single-pass tile: everybody has read s_tile before it changes
         // publish the next tile; if its dependency is not known to be satisfied yet, say so and take the
@@ -453,7 +444,7 @@ __global__ void __launch_bounds__(fused_threads<N1, N2>(), fused_min_blocks<N1, 
             // discards (fused transport: a fence there waits for NVLink round trips on the critical path of every tile) level B
             // signals without one.
 #ifndef HPXFFT_B200_DIAG_NOFENCE
-            if (r < A_PART || ctl.discard) __threadfence();
+            if (r < (unsigned) N2 || ctl.discard) __threadfence();
 #endif
             atomicAdd(done, 1u);
         }

@@ -50,11 +50,7 @@ int launch_cols_fused_t(const hpxfft_b200_plan *p, const InterView &in, const Co
     ctl.lag = p->lag;
     ctl.nslot = p->nslot;
     ctl.ct0 = ct0;
-    ctl.sg = p->col_sg ? p->col_sg : 1u;
-    {
-        const unsigned ngroups = (ntiles + ctl.sg - 1) / ctl.sg;
-        if (ctl.nslot > ngroups) ctl.nslot = ngroups; // a short chunk needs (and may use) no more slots than super-groups
-    }
+    if (ctl.nslot > ntiles) ctl.nslot = ntiles; // a short chunk needs (and may use) no more slots than strips
     {
         static const int discard = [] {
             const char *e = getenv("HPXFFT_B200_DISCARD");

@@ -302,43 +302,6 @@ void chunk_bounds(unsigned ntiles, unsigned w, int nch, int t, unsigned &t0, uns
     wc = cend > col0 ? cend - col0 : 0;
 }
 
-// strips per super-group, lag and ring slots (both counted in super-groups) of the fused column kernel
-void set_fused_pipeline(hpxfft_b200_plan *p)
-{
-    {
-        const int v = env_int("HPXFFT_B200_COL_SG", 1);
-        p->col_sg = (v == 2 || v == 4 || v == 8) ? (unsigned) v : 1u;
-    }
-    const unsigned per_group = p->col_sg * (p->n1 + p->n2);
-    if (p->col_sg == 1) {
-        p->lag = (unsigned) ((3 * (size_t) p->fused_grid / 2 + per_group - 1) / per_group) + 1;
-        p->nslot = 2 * p->lag + 1;
-    } else {
-        // A super-group is about as large as the number of resident CTAs, so a shorter pipeline suffices and keeps the ring
-        // (nslot * sg strips) inside L2: level B of super-group G is claimed `lag` groups after its level-A tiles (>= one group =
-        // more tiles than are ever in flight), and a slot is rewritten two groups after the level-B tiles that drained it were
-        // claimed.  nslot > lag is what rules out deadlock (dependencies only point to earlier-claimed tiles).
-        p->lag = (unsigned) ((p->fused_grid + per_group - 1) / per_group);
-        if (p->lag < 1) p->lag = 1;
-        p->nslot = p->lag + 2;
-    }
-    {
-        const int v = env_int("HPXFFT_B200_LAG", 0);
-        if (v >= 1) {
-            p->lag = (unsigned) v;
-            p->nslot = p->col_sg == 1 ? 2 * p->lag + 1 : p->lag + 1;
-        }
-    }
-    {
-        const int v = env_int("HPXFFT_B200_NSLOT", 0);
-        if (v > (int) p->lag) p->nslot = (unsigned) v;
-    }
-    {
-        const unsigned ngroups = (p->ntiles * p->col_split + p->col_sg - 1) / p->col_sg;
-        if (p->nslot > ngroups) p->nslot = ngroups > 0 ? ngroups : 1;
-    }
-}
-
 cudaEvent_t *event_set(hpxfft_b200_plan *p)
 {
     cudaEvent_t *ev = p->evs.data() + (size_t) (p->nrec % hpxfft_b200_plan::EV_SETS) * hpxfft_b200_plan::EV_PER_SET;
@@ -961,8 +924,19 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
             if (v >= 1 && v < bps) bps = v;
         }
         p->fused_grid = (unsigned) (bps * (p->sm_count - p->sm_reserve));
-        set_fused_pipeline(p);
-        p->bytesS = (size_t) p->nslot * p->col_sg * (p->nx / p->col_split) * CW * sizeof(cd);
+        const unsigned per_group = p->n1 + p->n2;
+        p->lag = (unsigned) ((3 * (size_t) p->fused_grid / 2 + per_group - 1) / per_group) + 1;
+        {
+            const int v = env_int("HPXFFT_B200_LAG", 0);
+            if (v >= 1) p->lag = (unsigned) v;
+        }
+        p->nslot = 2 * p->lag + 1;
+        {
+            const int v = env_int("HPXFFT_B200_NSLOT", 0);
+            if (v > (int) p->lag) p->nslot = (unsigned) v;
+        }
+        if (p->nslot > p->ntiles * p->col_split) p->nslot = p->ntiles > 0 ? p->ntiles * p->col_split : 1;
+        p->bytesS = (size_t) p->nslot * (p->nx / p->col_split) * CW * sizeof(cd);
     }
     if (p->transport == TR_NCCL || p->transport == TR_CE) {
         size_t tiles_all = 0;
@@ -1016,7 +990,7 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
         while (sr > 1 && (p->nxl % sr != 0 || p->nxl / sr < 8)) sr /= 2;
         if (!p->fused) sc = 1;
         unsigned min_tiles = p->ntiles_of[0]; // every rank but the last owns ntiles_of[0] strips; the last one at least as many
-        while (sc > 1 && min_tiles / sc < 2 * (p->lag + 1) * p->col_sg) sc /= 2;
+        while (sc > 1 && min_tiles / sc < 2 * (p->lag + 1)) sc /= 2;
         p->chunks_r = sr < 1 ? 1 : sr;
         p->chunks_c = sc < 1 ? 1 : sc;
         p->ev_chunk.assign((size_t) p->chunks_r + p->chunks_c, nullptr);
@@ -1498,8 +1472,11 @@ int hpxfft_b200_c2c_cols_variant(double *host_data, size_t n, size_t width, int 
             return rc;
         }
         p->fused_grid = (unsigned) (bps * p->sm_count);
-        set_fused_pipeline(p);
-        sbytes = (size_t) p->nslot * p->col_sg * (n / p->col_split) * CW * sizeof(cd);
+        const unsigned per_group = p->n1 + p->n2;
+        p->lag = (unsigned) ((3 * (size_t) p->fused_grid / 2 + per_group - 1) / per_group) + 1;
+        p->nslot = 2 * p->lag + 1;
+        if (p->nslot > p->ntiles * p->col_split) p->nslot = p->ntiles * p->col_split;
+        sbytes = (size_t) p->nslot * (n / p->col_split) * CW * sizeof(cd);
         CUC(cudaMalloc(&p->ctl, (1 + 2 * (size_t) p->ntiles * p->col_split) * sizeof(unsigned)));
     }
     if (p->two_level) CUC(cudaMalloc(&p->S, sbytes));

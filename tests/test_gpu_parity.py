@@ -126,21 +126,6 @@ def test_c2c_cols_32768_with_prestage(pkg, lib, oracle, monkeypatch):
     assert oracle.rel_l2(got.view(np.float64), np.ascontiguousarray(ref).view(np.float64)) <= 1e-13
 
 
-@pytest.mark.parametrize("sg", [2, 4])
-@pytest.mark.parametrize("n,width", [(512, 16 * 90 + 5), (4096, 16 * 45 + 3), (16384, 16 * 50 + 1), (32768, 16 * 24 + 7)])
-def test_c2c_cols_fused_super_groups(pkg, lib, oracle, monkeypatch, n, width, sg):
-    """HPXFFT_B200_COL_SG: tiles of `sg` adjacent strips are claimed interleaved (level-B stores of neighbouring strips land next to
-    each other in time); ragged last super-group, ring wrap-around."""
-    monkeypatch.setenv("HPXFFT_B200_COL_SG", str(sg))
-    rng = np.random.default_rng(n + width + sg)
-    a = rng.uniform(-1, 1, (n, width)) + 1j * rng.uniform(-1, 1, (n, width))
-    got = a.copy()
-    pkg.capi.check(lib.hpxfft_b200_c2c_cols_variant(got.ctypes.data, n, width, 0, 0))
-    import scipy.fft as sfft
-    ref = sfft.fft(a, axis=0, workers=8)
-    assert oracle.rel_l2(got.view(np.float64), np.ascontiguousarray(ref).view(np.float64)) <= 1e-13
-
-
 @pytest.mark.parametrize("n,width", [(512, 16 * 90 + 5), (4096, 16 * 45), (16384, 16 * 50 + 1), (32768, 16 * 24 + 7), (65536, 16 * 12)])
 def test_c2c_cols_fused_ring_wraps(pkg, lib, oracle, n, width):
     """More strips than scratch-ring slots: the level-A tiles reuse slots that level-B tiles have drained
