@@ -1,6 +1,7 @@
 // launch_rows.cu -- dispatch of the row (r2c) kernels.
 #include "kernels_rows_long.cuh"
 #include "kernels_rows_long2.cuh"
+#include "kernels_rows_dit2.cuh"
 #include "kernels_rows_v2.cuh"
 
 #include <cstdlib>
@@ -69,6 +70,18 @@ template <bool FAST> int launch_rows_long2_t(const hpxfft_b200_plan *p, const Ro
     return 0;
 }
 
+// ny = 32768, decimation in time: two v2-style halves by sample parity, Ze parked per thread in L2 (kernels_rows_dit2.cuh)
+template <bool FAST> int launch_rows_dit2_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+{
+    if (int rc = ensure_smem(rows_dit2_kernel<FAST>, rd2::SMEM, p->device)) return rc;
+    if (!p->zraw) return fail(HPXFFT_B200_ESTATE, "long-row scratch missing");
+    const unsigned cap = (unsigned) (p->sm_count - p->sm_reserve > 0 ? p->sm_count - p->sm_reserve : 1);
+    const unsigned grid = nrows < cap ? nrows : cap;
+    rows_dit2_kernel<FAST><<<grid, ROW_THREADS, rd2::SMEM, p->stream>>>(V, pitch, nrows, dst, p->tw_row, p->zraw);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // read per launch (cheap) so that the parity tests can select the variants in one process
 int rows_long_variant()
 {
@@ -117,7 +130,9 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
         if (rows_v1_path()) return launch_rows_big<8192>(p, dst, nrows, V, pitch);
         return dst.P == 1 ? launch_rows_v2_t<true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false>(p, dst, nrows, V, pitch);
     case 16384:
-        if (rows_long_variant() != 2) return launch_rows_long<2>(p, dst, nrows, V, pitch); // HPXFFT_B200_ROWS_LONG=1: generic long-row kernel
+        if (rows_long_variant() == 1) return launch_rows_long<2>(p, dst, nrows, V, pitch); // HPXFFT_B200_ROWS_LONG=1: generic long-row kernel
+        if (rows_long_variant() == 3) return dst.P == 1 ? launch_rows_dit2_t<true>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false>(p, dst, nrows, V, pitch);
+        if (rows_long_variant() == 4) return launch_rows_dit2_t<false>(p, dst, nrows, V, pitch); // general output addressing on one GPU (tests)
         return dst.P == 1 ? launch_rows_long2_t<true>(p, dst, nrows, V, pitch) : launch_rows_long2_t<false>(p, dst, nrows, V, pitch);
     case 32768: return launch_rows_long<4>(p, dst, nrows, V, pitch);
     case 65536: return launch_rows_long<8>(p, dst, nrows, V, pitch);

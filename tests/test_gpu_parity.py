@@ -95,6 +95,34 @@ def test_r2c_rows_selectable_variants(pkg, lib, oracle, monkeypatch, env, ny):
     assert oracle.rel_l2(got, np.ascontiguousarray(ref).view(np.longdouble).reshape(batch, -1)) <= 1e-13
 
 
+@pytest.mark.parametrize("variant", ["3", "4"])
+@pytest.mark.parametrize("batch", [5, 449])
+def test_r2c_rows_32768_decimation_in_time(pkg, lib, oracle, monkeypatch, variant, batch):
+    """rows_dit2_kernel (kernels_rows_dit2.cuh): ROWS_LONG=3 with the one-GPU output addressing, 4 with the general one that the
+    distributed slabs use; 449 rows = every persistent CTA walks several rows (scratch reuse, next-row staging), ragged last wave."""
+    monkeypatch.setenv("HPXFFT_B200_ROWS_LONG", variant)
+    ny = 32768
+    a = np.zeros((batch, ny + 2))
+    a[:, :ny] = np.random.default_rng(batch).uniform(-1, 1, (batch, ny))
+    got = a.copy()
+    pkg.capi.check(lib.hpxfft_b200_r2c_rows(got.ctypes.data, batch, ny + 2, 0))
+    import scipy.fft as sfft
+    ref = sfft.rfft(a[:, :ny], axis=1, workers=8)
+    assert oracle.rel_l2(got, np.ascontiguousarray(ref).view(np.float64).reshape(batch, -1)) <= 1e-13
+    if batch == 5:   # bin by bin against extended precision: no output may be missing or misplaced
+        refl = sfft.rfft(a[:, :ny].astype(np.longdouble), axis=1)
+        err = np.abs(got.view(np.complex128).reshape(batch, -1) - refl.astype(np.complex128))
+        assert err.max() <= 1e-9
+
+
+@pytest.mark.parametrize("variant", ["3", "4"])
+def test_2d_32768_rows_decimation_in_time(pkg, oracle, monkeypatch, variant):
+    monkeypatch.setenv("HPXFFT_B200_ROWS_LONG", variant)
+    a = oracle.make_input(320, 32768, oracle.PATTERN_UNIFORM, seed=11)
+    got, _ = shared_fft(pkg, a)
+    assert oracle.rel_l2(got, oracle.fft_2d_r2c_shared(a, workers=8)) <= TOL
+
+
 # variant 0 = what a plan launches: the persistent fused four-step kernel for n > 256, i.e. every (N1, N2) pair of
 # launch_fused.cu -- 512 (32,16), 1024 (32,32), 2048 (64,32), 4096 (64,64), 8192 (128,64), 16384 (128,128),
 # 32768 (256,128), 65536 (256,256), 131072 (512,256), 262144 (512,512); variant 1 = the unfused launches.

@@ -65,6 +65,15 @@ def test_rows_long2_parked_even_bins_and_pairs(n):             # kernels_rows_lo
     assert np.abs(mk.herm_split(np.fft.fft(z), n) - np.fft.rfft(x)).max() < 1e-11 * n
 
 
+@pytest.mark.parametrize("PP", [4, 16, 64])
+def test_rows_dit2_combine_covers_every_bin_once(PP):          # kernels_rows_dit2.cuh
+    n = 64 * PP
+    x = np.random.default_rng(PP).standard_normal(n)
+    X, cnt = mk.rows_dit2_model(x, PP)
+    assert (cnt == 1).all()
+    assert np.abs(X - np.fft.rfft(x)).max() < 1e-11 * n
+
+
 @pytest.mark.parametrize("t,q", [(7, 1), (3, 2), (5, 8), (3, 64), (13, 16), (31, 32), (9, 128)])
 def test_mixed_radix_rows(t, q):                               # kernels_generic.cuh: rows_mixed_kernel
     m = t * q

@@ -185,6 +185,68 @@ def rows_long2_model(x):
     return out
 
 
+def herm_pair(a, b, wv):
+    """kernels_rows.cuh: herm_pair(Z[k], Z[m-k], w_n^k) -> X[k], X[m-k]."""
+    s, d = a + np.conj(b), a - np.conj(b)
+    t = d * (0.5 * wv)
+    e = 0.5 * s
+    xk = complex(e.real + t.imag, e.imag - t.real)
+    xmk = complex(e.real - t.imag, -(e.imag + t.real))
+    return xk, xmk
+
+
+def rows_dit2_model(x, PP):
+    """kernels_rows_dit2.cuh: n = 4 M real points, M = 16 PP.  Decimation in time: Ze = FFT_M(z[2j]) is parked per thread, the
+    second half computes Zo = FFT_M(z[2j+1]) with the same thread <-> column mapping and every thread combines
+    {Ze, Zo}[k], {Ze, Zo}[M-k] into X[k], X[M-k], X[k+M], X[2M-k].  Returns (X, number of stores per bin)."""
+    n = len(x)
+    M = n // 4
+    assert M == 16 * PP
+    m = 2 * M
+    z = x[0::2] + 1j * x[1::2]
+    Ze, Zo = np.fft.fft(z[0::2]), np.fft.fft(z[1::2])
+    X = np.zeros(m + 1, complex)
+    cnt = np.zeros(m + 1, int)
+
+    def put(k, v):
+        X[k] = v
+        cnt[k] += 1
+
+    def four(k, ze_k, zo_k, ze_mk, zo_mk, second=True):
+        wm, wn = w(m, k), w(n, k)
+        P, Q = zo_k * wm, -(zo_mk * np.conj(wm))
+        xk, x2mk = herm_pair(ze_k + P, ze_mk - Q, wn)
+        put(k, xk)
+        put(2 * M - k, x2mk)
+        if second:
+            xkM, xMk = herm_pair(ze_k - P, ze_mk + Q, wn * -1j)
+            put(k + M, xkM)
+            put(M - k, xMk)
+
+    for lt in range(PP // 2):
+        jA = lt
+        if lt:
+            jB = PP - lt
+            for s in range(16):
+                k, mk_ = jA + s * PP, jB + (15 - s) * PP
+                assert k + mk_ == M
+                four(k, Ze[k], Zo[k], Ze[mk_], Zo[mk_])
+        else:
+            z0 = Ze[0] + Zo[0]                       # Z[0]; Z[M] = Ze[0] - Zo[0]
+            put(0, z0.real + z0.imag)
+            put(m, z0.real - z0.imag)
+            put(M, np.conj(Ze[0] - Zo[0]))
+            for s in range(1, 8):
+                k, mk_ = s * PP, (16 - s) * PP
+                four(k, Ze[k], Zo[k], Ze[mk_], Zo[mk_])
+            k = 8 * PP                               # M/2 is its own partner: X[M/2], X[3M/2]
+            four(k, Ze[k], Zo[k], Ze[k], Zo[k], second=False)
+            for s in range(8):
+                k, mk_ = PP // 2 + s * PP, PP // 2 + (15 - s) * PP
+                four(k, Ze[k], Zo[k], Ze[mk_], Zo[mk_])
+    return X, cnt
+
+
 def gen_rev(k, q, lg):
     """kernels_generic.cuh: position of F[k] after the in-place DIF passes (radix 4 ..., one radix 2 when lg is odd)."""
     pos, length = 0, q
