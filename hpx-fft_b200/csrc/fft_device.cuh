@@ -166,6 +166,12 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+// L2 prefetch issued by ONE thread through the bulk-copy (TMA) unit: unlike prefetch.global.L2 it does not occupy a slot of
+// the load/store queue per 32 bytes.  p and bytes must be multiples of 16.
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ cd ld_cg_hint(const cd *p, unsigned long long policy)
 {
     cd r;

@@ -43,7 +43,8 @@ __device__ __forceinline__ void combine4(cd ze_k, cd zo_k, cd ze_mk, cd zo_mk, c
 }
 }  // namespace rd2
 
-template <bool FASTADDR>
+// PF: bulk L2 prefetch of the next row of this CTA (see rows_r2c_v2_kernel)
+template <bool FASTADDR, bool PF = false>
 __global__ void __launch_bounds__(ROW_THREADS, 1)
     rows_dit2_kernel(const cd *__restrict__ V, unsigned pitch, unsigned nxl, RowDst dst, const cd *__restrict__ tw, cd *__restrict__ scratch)
 {
@@ -98,6 +99,11 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
         for (int h = 0; h < 2; ++h) {
             cp_async_wait_all();
             __syncthreads(); // (1) the sub-sequence has landed and is visible to every warp
+            if constexpr (PF) {
+                // the whole next row (both parities), issued while this row's second half is being transformed
+                if (h == 1 && lane == 0 && row + gridDim.x < nxl)
+                    l2_prefetch_bulk(V + (unsigned long long) (row + gridDim.x) * pitch + warp * (2 * M / 8), (unsigned) (2 * M / 8 * sizeof(cd)));
+            }
 
             // ---- pass A: radix 16 over j2 = u + 32 r for the two stride-16 sub-sequences of this warp, in place ----
             {

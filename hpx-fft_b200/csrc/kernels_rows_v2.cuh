@@ -31,7 +31,9 @@ constexpr size_t SMEM = (size_t) (LP + TW_ENTRIES) * sizeof(cd);
 __device__ __forceinline__ int pad(int p) { return p ^ (((p >> 4) ^ (p >> 9)) & 7); }
 }  // namespace rv2
 
-template <bool FASTADDR>
+// PF: one lane per warp asks the bulk-copy unit to pull the NEXT row of this CTA into L2 as soon as the current one has landed, so
+// that the cp.async refill two barriers later is served at L2 latency
+template <bool FASTADDR, bool PF = false>
 __global__ void __launch_bounds__(ROW_THREADS, 1)
     rows_r2c_v2_kernel(const cd *__restrict__ V, unsigned pitch, unsigned nxl, RowDst dst, const cd *__restrict__ tw)
 {
@@ -79,6 +81,10 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
 #endif
         cp_async_wait_all();
         __syncthreads(); // (1) the whole row has landed and is visible to every warp
+        if constexpr (PF) {
+            if (lane == 0 && row0 + gridDim.x < nxl)
+                l2_prefetch_bulk(row_ptr(row0 + gridDim.x) + warp * (M / 8), (unsigned) (M / 8 * sizeof(cd)));
+        }
 
         // ---- pass A: radix 16 over j2 = u + 32 r for the two sub-sequences of this warp, in place ----
         {

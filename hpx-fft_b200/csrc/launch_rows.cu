@@ -48,12 +48,12 @@ template <int C> int launch_rows_long(const hpxfft_b200_plan *p, const RowDst &d
 }
 
 // ny = 16384: warp-local in-place sub-FFTs (kernels_rows_v2.cuh); HPXFFT_B200_ROWS_V1=1 selects the Stockham kernel (A/B runs)
-template <bool FAST> int launch_rows_v2_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+template <bool FAST, bool PF> int launch_rows_v2_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
 {
-    if (int rc = ensure_smem(rows_r2c_v2_kernel<FAST>, rv2::SMEM, p->device)) return rc;
+    if (int rc = ensure_smem(rows_r2c_v2_kernel<FAST, PF>, rv2::SMEM, p->device)) return rc;
     const unsigned cap = (unsigned) (p->sm_count - p->sm_reserve > 0 ? p->sm_count - p->sm_reserve : 1);
     const unsigned grid = nrows < cap ? nrows : cap;
-    rows_r2c_v2_kernel<FAST><<<grid, ROW_THREADS, rv2::SMEM, p->stream>>>(V, pitch, nrows, dst, p->tw_row);
+    rows_r2c_v2_kernel<FAST, PF><<<grid, ROW_THREADS, rv2::SMEM, p->stream>>>(V, pitch, nrows, dst, p->tw_row);
     CU(cudaGetLastError());
     return 0;
 }
@@ -71,13 +71,13 @@ template <bool FAST> int launch_rows_long2_t(const hpxfft_b200_plan *p, const Ro
 }
 
 // ny = 32768, decimation in time: two v2-style halves by sample parity, Ze parked per thread in L2 (kernels_rows_dit2.cuh)
-template <bool FAST> int launch_rows_dit2_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+template <bool FAST, bool PF> int launch_rows_dit2_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
 {
-    if (int rc = ensure_smem(rows_dit2_kernel<FAST>, rd2::SMEM, p->device)) return rc;
+    if (int rc = ensure_smem(rows_dit2_kernel<FAST, PF>, rd2::SMEM, p->device)) return rc;
     if (!p->zraw) return fail(HPXFFT_B200_ESTATE, "long-row scratch missing");
     const unsigned cap = (unsigned) (p->sm_count - p->sm_reserve > 0 ? p->sm_count - p->sm_reserve : 1);
     const unsigned grid = nrows < cap ? nrows : cap;
-    rows_dit2_kernel<FAST><<<grid, ROW_THREADS, rd2::SMEM, p->stream>>>(V, pitch, nrows, dst, p->tw_row, p->zraw);
+    rows_dit2_kernel<FAST, PF><<<grid, ROW_THREADS, rd2::SMEM, p->stream>>>(V, pitch, nrows, dst, p->tw_row, p->zraw);
     CU(cudaGetLastError());
     return 0;
 }
@@ -87,6 +87,13 @@ int rows_long_variant()
 {
     const char *e = getenv("HPXFFT_B200_ROWS_LONG");
     return e ? atoi(e) : 2;
+}
+
+// HPXFFT_B200_ROWS_PF=1: bulk L2 prefetch of the next row (A/B runs)
+bool rows_prefetch()
+{
+    const char *e = getenv("HPXFFT_B200_ROWS_PF");
+    return e && e[0] == '1';
 }
 
 bool rows_v1_path()
@@ -128,11 +135,15 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
     case 4096: return launch_rows_big<4096>(p, dst, nrows, V, pitch);
     case 8192:
         if (rows_v1_path()) return launch_rows_big<8192>(p, dst, nrows, V, pitch);
-        return dst.P == 1 ? launch_rows_v2_t<true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false>(p, dst, nrows, V, pitch);
+        if (rows_prefetch()) return dst.P == 1 ? launch_rows_v2_t<true, true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, true>(p, dst, nrows, V, pitch);
+        return dst.P == 1 ? launch_rows_v2_t<true, false>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, false>(p, dst, nrows, V, pitch);
     case 16384:
         if (rows_long_variant() == 1) return launch_rows_long<2>(p, dst, nrows, V, pitch); // HPXFFT_B200_ROWS_LONG=1: generic long-row kernel
-        if (rows_long_variant() == 3) return dst.P == 1 ? launch_rows_dit2_t<true>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false>(p, dst, nrows, V, pitch);
-        if (rows_long_variant() == 4) return launch_rows_dit2_t<false>(p, dst, nrows, V, pitch); // general output addressing on one GPU (tests)
+        if (rows_long_variant() == 3) {
+            if (rows_prefetch()) return dst.P == 1 ? launch_rows_dit2_t<true, true>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false, true>(p, dst, nrows, V, pitch);
+            return dst.P == 1 ? launch_rows_dit2_t<true, false>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false, false>(p, dst, nrows, V, pitch);
+        }
+        if (rows_long_variant() == 4) return launch_rows_dit2_t<false, false>(p, dst, nrows, V, pitch); // general output addressing on one GPU (tests)
         return dst.P == 1 ? launch_rows_long2_t<true>(p, dst, nrows, V, pitch) : launch_rows_long2_t<false>(p, dst, nrows, V, pitch);
     case 32768: return launch_rows_long<4>(p, dst, nrows, V, pitch);
     case 65536: return launch_rows_long<8>(p, dst, nrows, V, pitch);
