@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libhpxfft_b200.so")
 UNITS = [("common.cu", (), ""), ("plan.cu", (), ""), ("launch_rows.cu", (), ""), ("launch_cols.cu", (), ""), ("launch_misc.cu", (), ""),
          ("launch_generic.cu", (), ""), ("launch_bluestein.cu", (), "")] + \
         [("launch_fused.cu", (f"HPXFFT_B200_FUSED_GROUP={g}",), f"_g{g}") for g in range(4)]
-HEADERS = ["fft_device.cuh", "layout.cuh", "kernels_rows.cuh", "kernels_rows_long.cuh", "kernels_rows_long2.cuh", "kernels_rows_dit2.cuh", "kernels_rows_v2.cuh", "kernels_cols.cuh", "kernels_misc.cuh", "kernels_generic.cuh", "kernels_bluestein.cuh",
+HEADERS = ["fft_device.cuh", "layout.cuh", "kernels_rows.cuh", "kernels_rows_long.cuh", "kernels_rows_long2.cuh", "kernels_rows_dit2.cuh", "kernels_rows_ditc.cuh", "kernels_rows_v2.cuh", "kernels_cols.cuh", "kernels_misc.cuh", "kernels_generic.cuh", "kernels_bluestein.cuh",
            "internal.h", "launch_util.h", os.path.join("..", "..", "include", "hpxfft_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -33,6 +33,76 @@ __device__ __forceinline__ void cp_async16_hint(cd *dst_smem, const cd *src_gmem
                  "l"(policy)
                  : "memory");
 }
+// The 8192-point core shared by the decimation-in-time kernels (same algebra as rows_r2c_v2_kernel, kernels_rows_v2.cuh).
+// passes_ab: the two warp-local in-place passes over the 16 stride-16 sub-sequences of the staged pencil.
+__device__ __forceinline__ void passes_ab(cd *sm, const cd *twA, int warp, int lane)
+{
+    // ---- pass A: radix 16 over j2 = u + 32 r for the two sub-sequences of this warp, in place ----
+    {
+        const int u = lane;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int j1 = 2 * warp + g;
+            cd *base = sm + ((j1 & 8) + 16 * u); // element j1 + 16 u + 512 r sits at (that & ~7) | ((j1 ^ u ^ r) & 7)
+            const int x = (j1 ^ u) & 7;
+            cd a[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) a[r] = base[512 * r + (x ^ (r & 7))];
+            fft_dif<16>(a);
+#pragma unroll
+            for (int s = 0; s < 16; ++s) {
+                cd o = a[bitrev(s, 4)];
+                if (s) o = cmul(o, twA[s * 32 + u]);
+                base[512 * s + (x ^ (s & 7))] = o;
+            }
+        }
+    }
+    __syncwarp(); // pass B reads what the other lanes of this warp just wrote
+    // ---- pass B: radix 32 over u for fixed s: one lane per (sub-sequence, s), in place ----
+    {
+        const int g = lane >> 4, s = lane & 15, j1 = 2 * warp + g;
+        cd *base = sm + ((j1 & 8) + 512 * s);
+        const int x = (j1 ^ s) & 7;
+        cd c[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) c[u] = base[16 * u + (x ^ (u & 7))];
+        fft_dif<32>(c);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) base[16 * t + (x ^ (t & 7))] = c[bitrev(t, 5)]; // F_j1[s + 16 t]
+    }
+}
+// last pass, part 1: the paired columns jA = lt and jB = PP - lt (lt = 0: PP/2) leave the pencil
+__device__ __forceinline__ void load_columns(const cd *sm, int lt, cd (&A)[16], cd (&B)[16])
+{
+    const int jA = lt, jB = lt ? PP - lt : PP / 2;
+    const cd *pa = sm + (16 * (jA >> 4) + 512 * (jA & 15));
+    const cd *pb = sm + (16 * (jB >> 4) + 512 * (jB & 15));
+    const int xa = ((jA >> 4) ^ jA) & 7, xb = ((jB >> 4) ^ jB) & 7;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        A[r] = pa[(r & 8) + (xa ^ (r & 7))];
+        B[r] = pb[(r & 8) + (xb ^ (r & 7))];
+    }
+}
+// last pass, part 2: radix 16 over j1.  Column jB gets the conjugate twiddles (w_M^(r (PP - j)) = w_16^r conj(w_M^(r j))): its
+// natural output s sits at butterfly output (s + 1) & 15; column jA (and both columns of lt = 0) at butterfly output s
+// (register bitrev(., 4)).
+__device__ __forceinline__ void finish_columns(const cd *tw2, int lt, cd (&A)[16], cd (&B)[16])
+{
+    if (lt != 0) {
+#pragma unroll
+        for (int r = 1; r < 16; ++r) {
+            const cd t = tw2[r * JW + lt];
+            A[r] = cmul(A[r], t);
+            B[r] = cmulc(B[r], t);
+        }
+    } else {
+#pragma unroll
+        for (int r = 1; r < 16; ++r) B[r] = mulw32(B[r], r); // jA = 0, jB = PP/2: w_M^(r PP/2) = w_32^r
+    }
+    fft_dif<16>(A);
+    fft_dif<16>(B);
+}
 // X[k], X[2M-k], X[k+M], X[M-k] from Ze/Zo at k and at M-k;  wm = w_m^k, wn = w_n^k (n = 4 M)
 __device__ __forceinline__ void combine4(cd ze_k, cd zo_k, cd ze_mk, cd zo_mk, cd wm, cd wn, cd &xk, cd &x2mk, cd &xkM, cd &xMk)
 {
@@ -105,75 +175,20 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
                     l2_prefetch_bulk(V + (unsigned long long) (row + gridDim.x) * pitch + warp * (2 * M / 8), (unsigned) (2 * M / 8 * sizeof(cd)));
             }
 
-            // ---- pass A: radix 16 over j2 = u + 32 r for the two stride-16 sub-sequences of this warp, in place ----
-            {
-                const int u = lane;
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int j1 = 2 * warp + g;
-                    cd *base = sm + ((j1 & 8) + 16 * u); // element j1 + 16 u + 512 r sits at (that & ~7) | ((j1 ^ u ^ r) & 7)
-                    const int x = (j1 ^ u) & 7;
-                    cd a[16];
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) a[r] = base[512 * r + (x ^ (r & 7))];
-                    fft_dif<16>(a);
-#pragma unroll
-                    for (int s = 0; s < 16; ++s) {
-                        cd o = a[bitrev(s, 4)];
-                        if (s) o = cmul(o, twA[s * 32 + u]);
-                        base[512 * s + (x ^ (s & 7))] = o;
-                    }
-                }
-            }
-            __syncwarp(); // pass B reads what the other lanes of this warp just wrote
-            // ---- pass B: radix 32 over u for fixed s: one lane per (sub-sequence, s), in place ----
-            {
-                const int g = lane >> 4, s = lane & 15, j1 = 2 * warp + g;
-                cd *base = sm + ((j1 & 8) + 512 * s);
-                const int x = (j1 ^ s) & 7;
-                cd c[32];
-#pragma unroll
-                for (int u = 0; u < 32; ++u) c[u] = base[16 * u + (x ^ (u & 7))];
-                fft_dif<32>(c);
-#pragma unroll
-                for (int t = 0; t < 32; ++t) base[16 * t + (x ^ (t & 7))] = c[bitrev(t, 5)]; // F_j1[s + 16 t]
-            }
+            passes_ab(sm, twA, warp, lane);
             __syncthreads(); // (2) all 16 sub-spectra are complete
 
             // ---- last pass: radix 16 over j1 on the paired columns jA = lt and jB = PP - lt (lt = 0: PP/2) ----
-            const int jA = lt, jB = lt ? PP - lt : PP / 2;
+            const int jA = lt;
             cd A[16], B[16];
-            {
-                const cd *pa = sm + (16 * (jA >> 4) + 512 * (jA & 15));
-                const cd *pb = sm + (16 * (jB >> 4) + 512 * (jB & 15));
-                const int xa = ((jA >> 4) ^ jA) & 7, xb = ((jB >> 4) ^ jB) & 7;
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    A[r] = pa[(r & 8) + (xa ^ (r & 7))];
-                    B[r] = pb[(r & 8) + (xb ^ (r & 7))];
-                }
-            }
+            load_columns(sm, lt, A, B);
             __syncthreads(); // (3) the pencil is dead: refill it with the other parity / the next row
             if (h == 0)
                 stage(V + (unsigned long long) row * pitch, 1);
             else if (row + gridDim.x < nxl)
                 stage(V + (unsigned long long) (row + gridDim.x) * pitch, 0);
 
-            // column jB gets the conjugate twiddles (w_M^(r (PP - j)) = w_16^r conj(w_M^(r j))): its natural output s sits at
-            // butterfly output (s + 1) & 15
-            if (lt != 0) {
-#pragma unroll
-                for (int r = 1; r < 16; ++r) {
-                    const cd t = tw2[r * JW + jA];
-                    A[r] = cmul(A[r], t);
-                    B[r] = cmulc(B[r], t);
-                }
-            } else {
-#pragma unroll
-                for (int r = 1; r < 16; ++r) B[r] = mulw32(B[r], r); // jA = 0, jB = PP/2: w_M^(r PP/2) = w_32^r
-            }
-            fft_dif<16>(A);
-            fft_dif<16>(B);
+            finish_columns(tw2, lt, A, B);
 
             if (h == 0) {
                 // park Ze in butterfly order; the second half reads slot i next to its own A[i] / B[i]

@@ -2,6 +2,7 @@
 #include "kernels_rows_long.cuh"
 #include "kernels_rows_long2.cuh"
 #include "kernels_rows_dit2.cuh"
+#include "kernels_rows_ditc.cuh"
 #include "kernels_rows_v2.cuh"
 
 #include <cstdlib>
@@ -82,6 +83,23 @@ template <bool FAST, bool PF> int launch_rows_dit2_t(const hpxfft_b200_plan *p, 
     return 0;
 }
 
+// ny = 2 C * 8192, decimation in time over C sample classes, all classes parked per thread (kernels_rows_ditc.cuh)
+template <int C, bool FAST> int launch_rows_ditc_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+{
+    constexpr size_t smem = rdc::smem_bytes<C>();
+    if (int rc = ensure_smem(rows_ditc_kernel<C, FAST>, smem, p->device)) return rc;
+    if (!p->zraw) return fail(HPXFFT_B200_ESTATE, "long-row scratch missing");
+    const unsigned cap = (unsigned) (p->sm_count - p->sm_reserve > 0 ? p->sm_count - p->sm_reserve : 1);
+    const unsigned grid = nrows < cap ? nrows : cap;
+    rows_ditc_kernel<C, FAST><<<grid, ROW_THREADS, smem, p->stream>>>(V, pitch, nrows, dst, p->tw_row, p->zraw);
+    CU(cudaGetLastError());
+    return 0;
+}
+template <int C> int launch_rows_ditc(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, bool general)
+{
+    return dst.P == 1 && !general ? launch_rows_ditc_t<C, true>(p, dst, nrows, V, pitch) : launch_rows_ditc_t<C, false>(p, dst, nrows, V, pitch);
+}
+
 // read per launch (cheap) so that the parity tests can select the variants in one process
 int rows_long_variant()
 {
@@ -138,6 +156,7 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
         if (rows_prefetch()) return dst.P == 1 ? launch_rows_v2_t<true, true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, true>(p, dst, nrows, V, pitch);
         return dst.P == 1 ? launch_rows_v2_t<true, false>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, false>(p, dst, nrows, V, pitch);
     case 16384:
+        if (rows_long_variant() == 5 || rows_long_variant() == 6) return launch_rows_ditc<2>(p, dst, nrows, V, pitch, rows_long_variant() == 6);
         if (rows_long_variant() == 1) return launch_rows_long<2>(p, dst, nrows, V, pitch); // HPXFFT_B200_ROWS_LONG=1: generic long-row kernel
         if (rows_long_variant() == 3) {
             if (rows_prefetch()) return dst.P == 1 ? launch_rows_dit2_t<true, true>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false, true>(p, dst, nrows, V, pitch);
@@ -145,8 +164,13 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
         }
         if (rows_long_variant() == 4) return launch_rows_dit2_t<false, false>(p, dst, nrows, V, pitch); // general output addressing on one GPU (tests)
         return dst.P == 1 ? launch_rows_long2_t<true>(p, dst, nrows, V, pitch) : launch_rows_long2_t<false>(p, dst, nrows, V, pitch);
-    case 32768: return launch_rows_long<4>(p, dst, nrows, V, pitch);
-    case 65536: return launch_rows_long<8>(p, dst, nrows, V, pitch);
+    // HPXFFT_B200_ROWS_LONG=5: decimation-in-time kernel (6: with the general output addressing on one GPU, for tests)
+    case 32768:
+        if (rows_long_variant() == 5 || rows_long_variant() == 6) return launch_rows_ditc<4>(p, dst, nrows, V, pitch, rows_long_variant() == 6);
+        return launch_rows_long<4>(p, dst, nrows, V, pitch);
+    case 65536:
+        if (rows_long_variant() == 5 || rows_long_variant() == 6) return launch_rows_ditc<8>(p, dst, nrows, V, pitch, rows_long_variant() == 6);
+        return launch_rows_long<8>(p, dst, nrows, V, pitch);
     default: return fail(HPXFFT_B200_EINVAL, "unsupported row length ny=%zu (ny/2 must be a power of two <= 65536)", 2 * m);
     }
 }

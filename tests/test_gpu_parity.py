@@ -115,6 +115,25 @@ def test_r2c_rows_32768_decimation_in_time(pkg, lib, oracle, monkeypatch, varian
         assert err.max() <= 1e-9
 
 
+@pytest.mark.parametrize("variant", ["5", "6"])
+@pytest.mark.parametrize("ny,batch", [(32768, 5), (32768, 449), (65536, 5), (65536, 301), (131072, 3), (131072, 160)])
+def test_r2c_rows_decimation_in_time_classes(pkg, lib, oracle, monkeypatch, variant, ny, batch):
+    """rows_ditc_kernel<C> (kernels_rows_ditc.cuh), C = 2, 4, 8: ROWS_LONG=5 with the one-GPU output addressing, 6 with the
+    general one; the larger batches make every persistent CTA walk several rows (scratch reuse, next-row gather in flight)."""
+    monkeypatch.setenv("HPXFFT_B200_ROWS_LONG", variant)
+    a = np.zeros((batch, ny + 2))
+    a[:, :ny] = np.random.default_rng(ny + batch).uniform(-1, 1, (batch, ny))
+    got = a.copy()
+    pkg.capi.check(lib.hpxfft_b200_r2c_rows(got.ctypes.data, batch, ny + 2, 0))
+    import scipy.fft as sfft
+    ref = sfft.rfft(a[:, :ny], axis=1, workers=8)
+    assert oracle.rel_l2(got, np.ascontiguousarray(ref).view(np.float64).reshape(batch, -1)) <= 1e-13
+    if batch <= 5:   # bin by bin against extended precision: no output may be missing or misplaced
+        refl = sfft.rfft(a[:, :ny].astype(np.longdouble), axis=1)
+        err = np.abs(got.view(np.complex128).reshape(batch, -1) - refl.astype(np.complex128))
+        assert err.max() <= 1e-9
+
+
 @pytest.mark.parametrize("variant", ["3", "4"])
 def test_2d_32768_rows_decimation_in_time(pkg, oracle, monkeypatch, variant):
     monkeypatch.setenv("HPXFFT_B200_ROWS_LONG", variant)

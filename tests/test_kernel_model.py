@@ -74,6 +74,15 @@ def test_rows_dit2_combine_covers_every_bin_once(PP):          # kernels_rows_di
     assert np.abs(X - np.fft.rfft(x)).max() < 1e-11 * n
 
 
+@pytest.mark.parametrize("C,PP", [(2, 4), (4, 4), (8, 4), (4, 16), (8, 16)])
+def test_rows_ditc_combine_covers_every_bin_once(C, PP):      # kernels_rows_ditc.cuh
+    n = 32 * C * PP
+    x = np.random.default_rng(C * PP).standard_normal(n)
+    X, cnt = mk.rows_ditc_model(x, C, PP)
+    assert (cnt == 1).all()
+    assert np.abs(X - np.fft.rfft(x)).max() < 1e-11 * n
+
+
 @pytest.mark.parametrize("t,q", [(7, 1), (3, 2), (5, 8), (3, 64), (13, 16), (31, 32), (9, 128)])
 def test_mixed_radix_rows(t, q):                               # kernels_generic.cuh: rows_mixed_kernel
     m = t * q

@@ -247,6 +247,59 @@ def rows_dit2_model(x, PP):
     return X, cnt
 
 
+def rows_ditc_model(x, C, PP):
+    """kernels_rows_ditc.cuh: n = 2 C M real points, M = 16 PP.  C classes by sample index mod C, Zc = FFT_M(z[C j + c]) parked per
+    thread; the combine forms, for a pair (k, M - k),  u_c = w_m^(c k) Zc[k],  v_c = conj(w_m^(c k)) Zc[M - k],  U = DFT_C(u),
+    V = DFT_C(v)  and  X[k + M q], X[(M - k) + M (C - 1 - q)] = herm_pair(U[q], V[(C - q) mod C], w_n^(k + M q)).
+    Returns (X, number of stores per bin)."""
+    n = len(x)
+    M = n // (2 * C)
+    assert M == 16 * PP
+    m = C * M
+    z = x[0::2] + 1j * x[1::2]
+    Zc = [np.fft.fft(z[c::C]) for c in range(C)]
+    X = np.zeros(m + 1, complex)
+    cnt = np.zeros(m + 1, int)
+
+    def put(k, v):
+        X[k] = v
+        cnt[k] += 1
+
+    tw = [w(n, i) for i in range(n)]                       # the plan's table
+    W = [tw[i * PP] for i in range(32 * C)]                # shared-memory table w_{32C}^i
+
+    def pair(k, mk_, nq, last_single=False):
+        # k and mk_ index the sub-spectra (mk_ = (M - k) mod M); the kernel factors the twiddles over k = j + s PP
+        j, s = k % PP, k // PP
+        wck = [tw[2 * c * j] * W[(2 * c * s) % (32 * C)] for c in range(C)]     # w_m^(c k)
+        assert all(abs(wck[c] - w(m, c * k)) < 1e-12 for c in range(C))
+        u = np.array([wck[c] * Zc[c][k] for c in range(C)])
+        v = np.array([np.conj(wck[c]) * Zc[c][mk_] for c in range(C)])
+        U = np.array([sum(w(C, c * q) * u[c] for c in range(C)) for q in range(C)])
+        Vv = np.array([sum(w(C, c * q) * v[c] for c in range(C)) for q in range(C)])
+        for q in range(nq):
+            wn = tw[j] * W[s] * W[16 * q]                                        # w_n^(k + M q)
+            assert abs(wn - w(n, k + M * q)) < 1e-12
+            xk, xmk = herm_pair(U[q], Vv[(C - q) % C], wn)
+            put(k + M * q, xk)
+            if not (last_single and q == nq - 1):
+                put((M - k) + M * (C - 1 - q), xmk)
+
+    for lt in range(PP // 2):
+        if lt:
+            for s in range(16):
+                k = lt + s * PP
+                pair(k, M - k, C)
+        else:
+            pair(0, 0, C // 2 + 1, last_single=True)      # bins M q: q = 0 gives X[0] and X[m]; q = C/2 is its own partner
+            for s in range(1, 8):
+                pair(s * PP, (16 - s) * PP, C)
+            pair(8 * PP, 8 * PP, C // 2)                   # k = M/2 is its own partner
+            for s in range(8):
+                pair(PP // 2 + s * PP, PP // 2 + (15 - s) * PP, C)
+    return X, cnt
+
+
 def gen_rev(k, q, lg):
     """kernels_generic.cuh: position of F[k] after the in-place DIF passes (radix 4 ..., one radix 2 when lg is odd)."""
     pos, length = 0, q
