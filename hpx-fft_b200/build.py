@@ -66,7 +66,28 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _units()))
     subprocess.run([nvcc] + ARCH + ["-shared", "-o", out] + objs + ["-ldl"], check=True, cwd=CSRC)
+    bad = suspicious_sass(out)
+    if bad:
+        os.replace(out, out + ".rejected")
+        raise RuntimeError("ptxas emitted LDGSTS with an unset uniform descriptor register (see suspicious_sass) in: " + ", ".join(bad))
     return out
+
+
+def suspicious_sass(lib: str = LIB) -> list:
+    """Kernels whose cp.async instructions use the `[R+URx], desc[URy]` form.  ptxas 12.9 produced it for one instantiation of
+    rows_ditc_kernel (hinted cp.async under uniform-register pressure) with URx / URy never written: the launch died on a B200
+    with "illegal instruction".  No kernel of this library needs that form, so its presence rejects the build."""
+    cuobjdump = os.path.join(os.path.dirname(_nvcc()), "cuobjdump")
+    if not os.path.exists(cuobjdump):
+        return []
+    sass = subprocess.run([cuobjdump, "-sass", lib], check=True, capture_output=True, text=True).stdout
+    bad, fn = set(), "?"
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+        elif "LDGSTS" in line and "+UR" in line.split("desc[")[0]:
+            bad.add(fn)
+    return sorted(bad)
 
 
 if __name__ == "__main__":

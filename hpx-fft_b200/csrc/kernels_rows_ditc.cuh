@@ -61,12 +61,17 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
 
     // stride-C gather of class c: thread lt copies elements lt + 256 e of the sub-sequence.  Neighbouring classes share
     // sectors: keep them in L2 (evict_last) until the last class has been through.
-    auto stage = [&](const cd *zrow, int c) {
-        const unsigned long long pol = c == C - 1 ? drop : keep;
+    // The hint is dropped for <8, false>: ptxas 12.9 emits its hinted LDGSTS with a descriptor register that is never written
+    // ("illegal instruction" on the device, seen on a B200); build.py scans the SASS of every kernel for that form.
+    constexpr bool HINTED = !(C == 8 && !FASTADDR);
+    auto stage = [&](const cd *zrow, int c, unsigned long long pol) {
 #pragma unroll
         for (int e = 0; e < ROW_PT; ++e) {
             const int p = lt + e * ROW_THREADS;
-            rd2::cp_async16_hint(sm + rd2::pad(p), zrow + C * p + c, pol);
+            if constexpr (HINTED)
+                rd2::cp_async16_hint(sm + rd2::pad(p), zrow + C * p + c, pol);
+            else
+                cp_async16(sm + rd2::pad(p), zrow + C * p + c);
         }
     };
     auto out_ptr = [&](unsigned row, unsigned k) -> cd * {
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
     };
     auto rev4 = [](int s) { return (int) (__brev((unsigned) s) >> 28); };
 
-    if (blockIdx.x < nxl) stage(V + (unsigned long long) blockIdx.x * pitch, 0);
+    if (blockIdx.x < nxl) stage(V + (unsigned long long) blockIdx.x * pitch, 0, keep);
 
     for (unsigned row = blockIdx.x; row < nxl; row += gridDim.x) {
 #pragma unroll 1
@@ -119,10 +124,12 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
             cd A[16], B[16];
             rd2::load_columns(sm, lt, A, B);
             __syncthreads(); // (3) the pencil is dead: refill it with the next class / the first class of the next row
-            if (c < C - 1)
-                stage(V + (unsigned long long) row * pitch, c + 1);
+            if (c < C - 2)
+                stage(V + (unsigned long long) row * pitch, c + 1, keep);
+            else if (c == C - 2)
+                stage(V + (unsigned long long) row * pitch, C - 1, drop);
             else if (row + gridDim.x < nxl)
-                stage(V + (unsigned long long) (row + gridDim.x) * pitch, 0);
+                stage(V + (unsigned long long) (row + gridDim.x) * pitch, 0, keep);
             rd2::finish_columns(tw2, lt, A, B);
             // park in butterfly order: slot i <- A[i], slot 16 + i <- B[i]
             cd *xc = xe + (size_t) c * 32 * ROW_THREADS;

@@ -100,18 +100,28 @@ template <int C> int launch_rows_ditc(const hpxfft_b200_plan *p, const RowDst &d
     return dst.P == 1 && !general ? launch_rows_ditc_t<C, true>(p, dst, nrows, V, pitch) : launch_rows_ditc_t<C, false>(p, dst, nrows, V, pitch);
 }
 
-// read per launch (cheap) so that the parity tests can select the variants in one process
+// Environment knobs, read per launch (cheap) so that the parity tests can select the variants in one process.
+// HPXFFT_B200_ROWS_LONG selects the kernel for rows longer than one pencil (ny >= 32768):
+//   unset / 0: default -- rows_dit2_kernel (ny = 32768), rows_ditc_kernel<4 | 8> (ny = 65536 | 131072)
+//   1: rows_long_kernel<C> (round-1 design: C passes over the row, assembly loop)      2: rows_long2_kernel (ny = 32768 only)
+//   3: rows_dit2_kernel (ny = 32768 only)                                                5: rows_ditc_kernel<C>
 int rows_long_variant()
 {
     const char *e = getenv("HPXFFT_B200_ROWS_LONG");
-    return e ? atoi(e) : 2;
+    return e ? atoi(e) : 0;
 }
-
-// HPXFFT_B200_ROWS_PF=1: bulk L2 prefetch of the next row (A/B runs)
-bool rows_prefetch()
+// HPXFFT_B200_ROWS_GENERAL=1: the general output addressing (the one the distributed slabs use) on one GPU -- for the tests
+bool rows_general()
+{
+    const char *e = getenv("HPXFFT_B200_ROWS_GENERAL");
+    return e && e[0] == '1';
+}
+// HPXFFT_B200_ROWS_PF=0|1: bulk L2 prefetch of the next row.  Default: on for ny = 32768 (6.76 vs 7.10 ms at 32768^2), off for
+// ny = 16384 (1.170 vs 1.153 ms at 16384^2).
+bool rows_prefetch(bool dflt)
 {
     const char *e = getenv("HPXFFT_B200_ROWS_PF");
-    return e && e[0] == '1';
+    return e ? e[0] == '1' : dflt;
 }
 
 bool rows_v1_path()
@@ -151,26 +161,27 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
     case 1024: return launch_rows_big<1024>(p, dst, nrows, V, pitch);
     case 2048: return launch_rows_big<2048>(p, dst, nrows, V, pitch);
     case 4096: return launch_rows_big<4096>(p, dst, nrows, V, pitch);
-    case 8192:
+    case 8192: {
         if (rows_v1_path()) return launch_rows_big<8192>(p, dst, nrows, V, pitch);
-        if (rows_prefetch()) return dst.P == 1 ? launch_rows_v2_t<true, true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, true>(p, dst, nrows, V, pitch);
-        return dst.P == 1 ? launch_rows_v2_t<true, false>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, false>(p, dst, nrows, V, pitch);
-    case 16384:
-        if (rows_long_variant() == 5 || rows_long_variant() == 6) return launch_rows_ditc<2>(p, dst, nrows, V, pitch, rows_long_variant() == 6);
-        if (rows_long_variant() == 1) return launch_rows_long<2>(p, dst, nrows, V, pitch); // HPXFFT_B200_ROWS_LONG=1: generic long-row kernel
-        if (rows_long_variant() == 3) {
-            if (rows_prefetch()) return dst.P == 1 ? launch_rows_dit2_t<true, true>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false, true>(p, dst, nrows, V, pitch);
-            return dst.P == 1 ? launch_rows_dit2_t<true, false>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false, false>(p, dst, nrows, V, pitch);
-        }
-        if (rows_long_variant() == 4) return launch_rows_dit2_t<false, false>(p, dst, nrows, V, pitch); // general output addressing on one GPU (tests)
-        return dst.P == 1 ? launch_rows_long2_t<true>(p, dst, nrows, V, pitch) : launch_rows_long2_t<false>(p, dst, nrows, V, pitch);
-    // HPXFFT_B200_ROWS_LONG=5: decimation-in-time kernel (6: with the general output addressing on one GPU, for tests)
+        const bool fast = dst.P == 1 && !rows_general();
+        if (rows_prefetch(false)) return fast ? launch_rows_v2_t<true, true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, true>(p, dst, nrows, V, pitch);
+        return fast ? launch_rows_v2_t<true, false>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, false>(p, dst, nrows, V, pitch);
+    }
+    case 16384: {
+        const int v = rows_long_variant();
+        const bool fast = dst.P == 1 && !rows_general();
+        if (v == 1) return launch_rows_long<2>(p, dst, nrows, V, pitch);
+        if (v == 2) return fast ? launch_rows_long2_t<true>(p, dst, nrows, V, pitch) : launch_rows_long2_t<false>(p, dst, nrows, V, pitch);
+        if (v == 5) return launch_rows_ditc<2>(p, dst, nrows, V, pitch, !fast);
+        if (rows_prefetch(true)) return fast ? launch_rows_dit2_t<true, true>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false, true>(p, dst, nrows, V, pitch);
+        return fast ? launch_rows_dit2_t<true, false>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false, false>(p, dst, nrows, V, pitch);
+    }
     case 32768:
-        if (rows_long_variant() == 5 || rows_long_variant() == 6) return launch_rows_ditc<4>(p, dst, nrows, V, pitch, rows_long_variant() == 6);
-        return launch_rows_long<4>(p, dst, nrows, V, pitch);
+        if (rows_long_variant() == 1) return launch_rows_long<4>(p, dst, nrows, V, pitch);
+        return launch_rows_ditc<4>(p, dst, nrows, V, pitch, rows_general());
     case 65536:
-        if (rows_long_variant() == 5 || rows_long_variant() == 6) return launch_rows_ditc<8>(p, dst, nrows, V, pitch, rows_long_variant() == 6);
-        return launch_rows_long<8>(p, dst, nrows, V, pitch);
+        if (rows_long_variant() == 1) return launch_rows_long<8>(p, dst, nrows, V, pitch);
+        return launch_rows_ditc<8>(p, dst, nrows, V, pitch, rows_general());
     default: return fail(HPXFFT_B200_EINVAL, "unsupported row length ny=%zu (ny/2 must be a power of two <= 65536)", 2 * m);
     }
 }

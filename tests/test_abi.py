@@ -71,3 +71,13 @@ def test_partition(lib):
             assert a + wa == b and wa == cy // P
         assert cover[-1][0] + cover[-1][1] == cy  # last rank absorbs cy mod P: nothing is dropped
     assert lib.hpxfft_b200_partition(3, 4, 0, C.byref(c0), C.byref(w)) != 0
+
+
+def test_no_kernel_uses_the_miscompiled_cp_async_form(pkg, lib):
+    """build.py rejects a library whose SASS contains cp.async (LDGSTS) with an unset uniform descriptor register -- the form
+    ptxas 12.9 emitted once for a hinted cp.async and that faulted on a B200 with "illegal instruction"."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("hpxfft_b200_build", os.path.join(ROOT, "hpx-fft_b200", "build.py"))
+    build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(build)
+    assert build.suspicious_sass() == []

@@ -78,11 +78,17 @@ def test_r2c_rows(pkg, lib, oracle, ny):
     assert oracle.rel_l2(got, np.ascontiguousarray(ref).view(np.longdouble).reshape(batch, -1)) <= 1e-13
 
 
-@pytest.mark.parametrize("env,ny", [({"HPXFFT_B200_ROWS_V1": "1"}, 16384), ({"HPXFFT_B200_ROWS_LONG": "1"}, 32768)])
+@pytest.mark.parametrize("env,ny", [({"HPXFFT_B200_ROWS_V1": "1"}, 16384), ({"HPXFFT_B200_ROWS_PF": "1"}, 16384),
+                                    ({"HPXFFT_B200_ROWS_GENERAL": "1"}, 16384),
+                                    ({"HPXFFT_B200_ROWS_LONG": "1"}, 32768), ({"HPXFFT_B200_ROWS_LONG": "2"}, 32768),
+                                    ({"HPXFFT_B200_ROWS_LONG": "2", "HPXFFT_B200_ROWS_GENERAL": "1"}, 32768),
+                                    ({"HPXFFT_B200_ROWS_PF": "0"}, 32768),
+                                    ({"HPXFFT_B200_ROWS_LONG": "1"}, 65536), ({"HPXFFT_B200_ROWS_LONG": "1"}, 131072)])
 def test_r2c_rows_selectable_variants(pkg, lib, oracle, monkeypatch, env, ny):
-    """The row kernels that are not the default for their length stay selectable for A/B runs and stay correct:
-    ROWS_V1: the Stockham kernel rows_r2c_kernel<8192> for ny = 16384 (default: rows_r2c_v2_kernel);
-    ROWS_LONG=1: the generic long-row kernel rows_long_kernel<2> for ny = 32768 (default: rows_long2_kernel)."""
+    """The row kernels that are not the default for their length stay selectable for A/B runs and stay correct (launch_rows.cu):
+    ROWS_V1: the Stockham kernel rows_r2c_kernel<8192> for ny = 16384 (default: rows_r2c_v2_kernel); ROWS_PF: bulk L2 prefetch of
+    the next row on / off; ROWS_GENERAL: the distributed slabs' output addressing on one GPU;
+    ROWS_LONG=1: rows_long_kernel<C>, 2: rows_long2_kernel (ny = 32768) -- the defaults are the decimation-in-time kernels."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     batch = 5
@@ -95,32 +101,16 @@ def test_r2c_rows_selectable_variants(pkg, lib, oracle, monkeypatch, env, ny):
     assert oracle.rel_l2(got, np.ascontiguousarray(ref).view(np.longdouble).reshape(batch, -1)) <= 1e-13
 
 
-@pytest.mark.parametrize("variant", ["3", "4"])
-@pytest.mark.parametrize("batch", [5, 449])
-def test_r2c_rows_32768_decimation_in_time(pkg, lib, oracle, monkeypatch, variant, batch):
-    """rows_dit2_kernel (kernels_rows_dit2.cuh): ROWS_LONG=3 with the one-GPU output addressing, 4 with the general one that the
-    distributed slabs use; 449 rows = every persistent CTA walks several rows (scratch reuse, next-row staging), ragged last wave."""
+@pytest.mark.parametrize("general", ["0", "1"])
+@pytest.mark.parametrize("ny,batch,variant", [(32768, 5, "0"), (32768, 449, "0"), (32768, 5, "5"), (32768, 449, "5"),
+                                               (65536, 5, "0"), (65536, 301, "0"), (131072, 3, "0"), (131072, 160, "0")])
+def test_r2c_rows_decimation_in_time(pkg, lib, oracle, monkeypatch, general, ny, batch, variant):
+    """The default long-row kernels: rows_dit2_kernel (ny = 32768, kernels_rows_dit2.cuh) and rows_ditc_kernel<C> (C = 4, 8;
+    C = 2 with ROWS_LONG=5; kernels_rows_ditc.cuh), with the one-GPU output addressing and with the general one that the
+    distributed slabs use.  The larger batches make every persistent CTA walk several rows (scratch reuse, next-row gather in
+    flight, ragged last wave)."""
     monkeypatch.setenv("HPXFFT_B200_ROWS_LONG", variant)
-    ny = 32768
-    a = np.zeros((batch, ny + 2))
-    a[:, :ny] = np.random.default_rng(batch).uniform(-1, 1, (batch, ny))
-    got = a.copy()
-    pkg.capi.check(lib.hpxfft_b200_r2c_rows(got.ctypes.data, batch, ny + 2, 0))
-    import scipy.fft as sfft
-    ref = sfft.rfft(a[:, :ny], axis=1, workers=8)
-    assert oracle.rel_l2(got, np.ascontiguousarray(ref).view(np.float64).reshape(batch, -1)) <= 1e-13
-    if batch == 5:   # bin by bin against extended precision: no output may be missing or misplaced
-        refl = sfft.rfft(a[:, :ny].astype(np.longdouble), axis=1)
-        err = np.abs(got.view(np.complex128).reshape(batch, -1) - refl.astype(np.complex128))
-        assert err.max() <= 1e-9
-
-
-@pytest.mark.parametrize("variant", ["5", "6"])
-@pytest.mark.parametrize("ny,batch", [(32768, 5), (32768, 449), (65536, 5), (65536, 301), (131072, 3), (131072, 160)])
-def test_r2c_rows_decimation_in_time_classes(pkg, lib, oracle, monkeypatch, variant, ny, batch):
-    """rows_ditc_kernel<C> (kernels_rows_ditc.cuh), C = 2, 4, 8: ROWS_LONG=5 with the one-GPU output addressing, 6 with the
-    general one; the larger batches make every persistent CTA walk several rows (scratch reuse, next-row gather in flight)."""
-    monkeypatch.setenv("HPXFFT_B200_ROWS_LONG", variant)
+    monkeypatch.setenv("HPXFFT_B200_ROWS_GENERAL", general)
     a = np.zeros((batch, ny + 2))
     a[:, :ny] = np.random.default_rng(ny + batch).uniform(-1, 1, (batch, ny))
     got = a.copy()
@@ -134,9 +124,9 @@ def test_r2c_rows_decimation_in_time_classes(pkg, lib, oracle, monkeypatch, vari
         assert err.max() <= 1e-9
 
 
-@pytest.mark.parametrize("variant", ["3", "4"])
-def test_2d_32768_rows_decimation_in_time(pkg, oracle, monkeypatch, variant):
-    monkeypatch.setenv("HPXFFT_B200_ROWS_LONG", variant)
+@pytest.mark.parametrize("general", ["0", "1"])
+def test_2d_32768_rows_decimation_in_time(pkg, oracle, monkeypatch, general):
+    monkeypatch.setenv("HPXFFT_B200_ROWS_GENERAL", general)
     a = oracle.make_input(320, 32768, oracle.PATTERN_UNIFORM, seed=11)
     got, _ = shared_fft(pkg, a)
     assert oracle.rel_l2(got, oracle.fft_2d_r2c_shared(a, workers=8)) <= TOL
