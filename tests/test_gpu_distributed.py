@@ -41,6 +41,8 @@ def _worker(rank, world, port, q):
         cases = CASES + [(world, 32)]                       # n_x_local == 1
         if os.environ.get("HPXFFT_B200_DIST_CASES") == "fast":   # 8-GPU box time is expensive: one case per kernel family
             cases = [(64, 64), (1024, 2048), (64, 32768), (32768, 64), (296, 16384), (world, 32)]
+        if os.environ.get("HPXFFT_B200_DIST_CASES") == "rows":   # the long-row kernels with several destination ranks
+            cases = [(64, 32768), (32, 65536), (16, 131072), (296, 16384)]
         for (nx, ny) in cases:
             nxl = nx // world
             full = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=11)   # x-dependent input
@@ -62,7 +64,7 @@ def _worker(rank, world, port, q):
         # opt-in pipelined exchange (row chunks / strip chunks on a second stream)
         os.environ["HPXFFT_B200_CHUNKS"] = "4"
         os.environ["HPXFFT_B200_A2A"] = "nccl"
-        for (nx, ny) in PIPELINED_CASES:
+        for (nx, ny) in ([] if os.environ.get("HPXFFT_B200_DIST_CASES") == "rows" else PIPELINED_CASES):
             nxl = nx // world
             full = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=12)
             ref = oracle.fft_2d_r2c_shared(full, workers=2)
