@@ -147,6 +147,11 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
     if (p->rows_mixed) return launch_rows_mixed(p, dst, nrows, V, pitch, m);
     if (p->rows_blue) return launch_rows_blue(p, dst, nrows, V, pitch);
     if (p->rows_generic) return launch_rows_generic(p, dst, nrows, V, pitch, m);
+    // Fused transport: the kernel's stores cross NVLink.  The mirrored bin families of the decimation-in-time kernels start one
+    // bin off a 512-byte boundary, so every warp store leaves a 16-byte straggler; L2 merges those for local stores, a peer
+    // window does not (32768^2 on 2 GPUs: rows 6.97 ms against 3.9 ms with rows_long2_kernel, whose pair stores are aligned).
+    // Rows whose output leaves the GPU therefore keep the round-1/2 kernels with aligned 1 KB / 512-byte warp stores.
+    const bool remote = dst.P > 1 && p->transport == TR_FUSED;
     switch (m) {
     case 1: return launch_rows_tiny<1>(p, dst, nrows, V, pitch);
     case 2: return launch_rows_tiny<2>(p, dst, nrows, V, pitch);
@@ -171,16 +176,16 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
         const int v = rows_long_variant();
         const bool fast = dst.P == 1 && !rows_general();
         if (v == 1) return launch_rows_long<2>(p, dst, nrows, V, pitch);
-        if (v == 2) return fast ? launch_rows_long2_t<true>(p, dst, nrows, V, pitch) : launch_rows_long2_t<false>(p, dst, nrows, V, pitch);
+        if (v == 2 || (v == 0 && remote)) return fast ? launch_rows_long2_t<true>(p, dst, nrows, V, pitch) : launch_rows_long2_t<false>(p, dst, nrows, V, pitch);
         if (v == 5) return launch_rows_ditc<2>(p, dst, nrows, V, pitch, !fast);
         if (rows_prefetch(true)) return fast ? launch_rows_dit2_t<true, true>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false, true>(p, dst, nrows, V, pitch);
         return fast ? launch_rows_dit2_t<true, false>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false, false>(p, dst, nrows, V, pitch);
     }
     case 32768:
-        if (rows_long_variant() == 1) return launch_rows_long<4>(p, dst, nrows, V, pitch);
+        if (rows_long_variant() == 1 || (rows_long_variant() == 0 && remote)) return launch_rows_long<4>(p, dst, nrows, V, pitch);
         return launch_rows_ditc<4>(p, dst, nrows, V, pitch, rows_general());
     case 65536:
-        if (rows_long_variant() == 1) return launch_rows_long<8>(p, dst, nrows, V, pitch);
+        if (rows_long_variant() == 1 || (rows_long_variant() == 0 && remote)) return launch_rows_long<8>(p, dst, nrows, V, pitch);
         return launch_rows_ditc<8>(p, dst, nrows, V, pitch, rows_general());
     default: return fail(HPXFFT_B200_EINVAL, "unsupported row length ny=%zu (ny/2 must be a power of two <= 65536)", 2 * m);
     }
