@@ -147,11 +147,13 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
     if (p->rows_mixed) return launch_rows_mixed(p, dst, nrows, V, pitch, m);
     if (p->rows_blue) return launch_rows_blue(p, dst, nrows, V, pitch);
     if (p->rows_generic) return launch_rows_generic(p, dst, nrows, V, pitch, m);
-    // Fused transport: the kernel's stores cross NVLink.  The mirrored bin families of the decimation-in-time kernels start one
-    // bin off a 512-byte boundary, so every warp store leaves a 16-byte straggler; L2 merges those for local stores, a peer
-    // window does not (32768^2 on 2 GPUs: rows 6.97 ms against 3.9 ms with rows_long2_kernel, whose pair stores are aligned).
-    // Rows whose output leaves the GPU therefore keep the round-1/2 kernels with aligned 1 KB / 512-byte warp stores.
-    const bool remote = dst.P > 1 && p->transport == TR_FUSED;
+    // Several destination ranks (P > 1): measured on 2 GPUs at 32768^2, rows_dit2_kernel<false> runs at half its one-GPU rate
+    // (rows 6.97 ms over the fused transport and 7.09 ms into the local staging buffer of the copy-engine transport, against
+    // 3.6 / 4.4 ms for rows_long2_kernel; profiles/r2_t_bench_n2.json, r2_u_bench_n2_ce.json) -- cause not isolated (per-store
+    // destination-rank arithmetic; mirrored bin families that start one bin off a 512-byte boundary).  Until it is, slabs with
+    // several destination ranks keep the kernels that were measured at N = 2, 4, 8; HPXFFT_B200_ROWS_LONG=3 / 5 still forces
+    // the decimation-in-time kernels there (the distributed parity tests do).
+    const bool remote = dst.P > 1;
     switch (m) {
     case 1: return launch_rows_tiny<1>(p, dst, nrows, V, pitch);
     case 2: return launch_rows_tiny<2>(p, dst, nrows, V, pitch);

@@ -41,9 +41,19 @@ def _worker(rank, world, port, q):
         cases = CASES + [(world, 32)]                       # n_x_local == 1
         if os.environ.get("HPXFFT_B200_DIST_CASES") == "fast":   # 8-GPU box time is expensive: one case per kernel family
             cases = [(64, 64), (1024, 2048), (64, 32768), (32768, 64), (296, 16384), (world, 32)]
+        # the decimation-in-time long-row kernels are the one-GPU default; with several destination ranks they are opt-in
+        # (launch_rows.cu) and stay covered here: ROWS_LONG=3 (ny = 32768), 5 (ny = 65536, 131072)
+        forced = [(64, 32768, "3"), (64, 32768, "5"), (32, 65536, "5"), (16, 131072, "5")]
         if os.environ.get("HPXFFT_B200_DIST_CASES") == "rows":   # the long-row kernels with several destination ranks
             cases = [(64, 32768), (32, 65536), (16, 131072), (296, 16384)]
-        for (nx, ny) in cases:
+        elif os.environ.get("HPXFFT_B200_DIST_CASES") == "fast":
+            forced = forced[:1]
+        for case in cases + forced:
+            nx, ny = case[0], case[1]
+            if len(case) > 2:
+                os.environ["HPXFFT_B200_ROWS_LONG"] = case[2]
+            else:
+                os.environ.pop("HPXFFT_B200_ROWS_LONG", None)
             nxl = nx // world
             full = oracle.make_input(nx, ny, oracle.PATTERN_UNIFORM, seed=11)   # x-dependent input
             ref = oracle.fft_2d_r2c_shared(full, workers=2)
@@ -61,6 +71,7 @@ def _worker(rank, world, port, q):
                 results.append((nx, ny, comm, err * scale, fft.get_measurement("total")))
                 del fft
                 dist.barrier()
+        os.environ.pop("HPXFFT_B200_ROWS_LONG", None)
         # opt-in pipelined exchange (row chunks / strip chunks on a second stream)
         os.environ["HPXFFT_B200_CHUNKS"] = "4"
         os.environ["HPXFFT_B200_A2A"] = "nccl"
