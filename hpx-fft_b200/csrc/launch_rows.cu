@@ -147,13 +147,17 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
     if (p->rows_mixed) return launch_rows_mixed(p, dst, nrows, V, pitch, m);
     if (p->rows_blue) return launch_rows_blue(p, dst, nrows, V, pitch);
     if (p->rows_generic) return launch_rows_generic(p, dst, nrows, V, pitch, m);
-    // Several destination ranks (P > 1): measured on 2 GPUs at 32768^2, rows_dit2_kernel<false> runs at half its one-GPU rate
-    // (rows 6.97 ms over the fused transport and 7.09 ms into the local staging buffer of the copy-engine transport, against
-    // 3.6 / 4.4 ms for rows_long2_kernel; profiles/r2_t_bench_n2.json, r2_u_bench_n2_ce.json) -- cause not isolated (per-store
-    // destination-rank arithmetic; mirrored bin families that start one bin off a 512-byte boundary).  Until it is, slabs with
-    // several destination ranks keep the kernels that were measured at N = 2, 4, 8; HPXFFT_B200_ROWS_LONG=3 / 5 still forces
-    // the decimation-in-time kernels there (the distributed parity tests do).
-    const bool remote = dst.P > 1;
+    // Several destination ranks (P > 1).
+    // ny = 32768: the general-addressing instantiation rows_dit2_kernel<false> runs at half the rate of <true> -- 12.7 against
+    // 6.8 ms for 32768 rows on one GPU (profiles/r2_w_bench_32768_general_v0.json), 6.97 / 7.09 ms per 16384-row slab on 2 GPUs
+    // over the fused / copy-engine transports -- while rows_long2_kernel<false> loses 5 % (7.9 ms, 3.6 ms per slab).  Slabs with
+    // several destination ranks therefore keep rows_long2_kernel.
+    // ny = 65536 / 131072: rows_ditc_kernel<C, false> loses 3 % (3.82 against 3.70 ms, 2048 x 131072) and stays the default
+    // unless its stores cross NVLink (fused transport): its mirrored bin families start one bin off a 512-byte boundary, every
+    // warp store leaves a 16-byte straggler that L2 merges for local stores and a peer window does not, and that case has not
+    // been measured -- it keeps rows_long_kernel<C>, whose mirrored warp stores are aligned.
+    // HPXFFT_B200_ROWS_LONG=3 / 5 forces the decimation-in-time kernels anyway (the distributed parity tests do).
+    const bool multi = dst.P > 1, remote = multi && p->transport == TR_FUSED;
     switch (m) {
     case 1: return launch_rows_tiny<1>(p, dst, nrows, V, pitch);
     case 2: return launch_rows_tiny<2>(p, dst, nrows, V, pitch);
@@ -178,7 +182,7 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
         const int v = rows_long_variant();
         const bool fast = dst.P == 1 && !rows_general();
         if (v == 1) return launch_rows_long<2>(p, dst, nrows, V, pitch);
-        if (v == 2 || (v == 0 && remote)) return fast ? launch_rows_long2_t<true>(p, dst, nrows, V, pitch) : launch_rows_long2_t<false>(p, dst, nrows, V, pitch);
+        if (v == 2 || (v == 0 && multi)) return fast ? launch_rows_long2_t<true>(p, dst, nrows, V, pitch) : launch_rows_long2_t<false>(p, dst, nrows, V, pitch);
         if (v == 5) return launch_rows_ditc<2>(p, dst, nrows, V, pitch, !fast);
         if (rows_prefetch(true)) return fast ? launch_rows_dit2_t<true, true>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false, true>(p, dst, nrows, V, pitch);
         return fast ? launch_rows_dit2_t<true, false>(p, dst, nrows, V, pitch) : launch_rows_dit2_t<false, false>(p, dst, nrows, V, pitch);
