@@ -33,7 +33,9 @@ __device__ __forceinline__ int pad(int p) { return p ^ (((p >> 4) ^ (p >> 9)) & 
 
 // PF: one lane per warp asks the bulk-copy unit to pull the NEXT row of this CTA into L2 as soon as the current one has landed, so
 // that the cp.async refill two barriers later is served at L2 latency
-template <bool FASTADDR, bool PF = false>
+// ILV: the 32 cp.async of the refill are issued in four groups between the register-only steps of the tail (twiddles, the two
+// butterflies) instead of one burst: a burst backs up the load/store queue and stalls all eight warps at the same time
+template <bool FASTADDR, bool PF = false, bool ILV = false>
 __global__ void __launch_bounds__(ROW_THREADS, 1)
     rows_r2c_v2_kernel(const cd *__restrict__ V, unsigned pitch, unsigned nxl, RowDst dst, const cd *__restrict__ tw)
 {
@@ -64,13 +66,26 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
         return V + (unsigned long long) row * pitch;
     };
     // coalesced staging: thread lt copies elements lt + 256 e
-    auto stage = [&](const cd *zrow) {
+    auto stage_part = [&](const cd *zrow, int e0, int e1) {
 #pragma unroll
-        for (int e = 0; e < ROW_PT; ++e) {
+        for (int e = e0; e < e1; ++e) {
             const int p = lt + e * ROW_THREADS;
             cp_async16(sm + pad(p), zrow + p);
         }
     };
+    // Eight copies that must not be issued before `after[8..15]` exist.  ptxas schedules the inlined cp.async freely among
+    // register-only arithmetic (operand constraints of the asm statement do not survive into PTX), and packs the groups back into
+    // one burst; a true data dependence is the only thing it honours, so the source address of copy i carries a term that is zero
+    // at run time (pitch < 2^31) but that the compiler cannot fold: (high word of after[8 + i].x) & (pitch >> 31).
+    auto stage_after = [&](const cd *zrow, int e0, const cd (&after)[16]) {
+        const unsigned never = pitch >> 31;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int p = lt + (e0 + i) * ROW_THREADS;
+            cp_async16(sm + pad(p), zrow + p + ((unsigned) __double2hiint(after[8 + i].x) & never));
+        }
+    };
+    auto stage = [&](const cd *zrow) { stage_part(zrow, 0, ROW_PT); };
     if (blockIdx.x < nxl) stage(row_ptr(blockIdx.x));
 
     for (unsigned row0 = blockIdx.x; row0 < nxl; row0 += gridDim.x) {
@@ -137,7 +152,14 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
             }
         }
         __syncthreads(); // (3) the pencil buffer is dead: refill it with the next row while this one finishes in registers
-        if (row0 + gridDim.x < nxl) stage(row_ptr(row0 + gridDim.x));
+        const bool refill = row0 + gridDim.x < nxl;
+        const cd *znext = row_ptr(refill ? row0 + gridDim.x : row0);
+        if (refill) {
+            if constexpr (ILV)
+                stage_part(znext, 0, ROW_PT / 4);
+            else
+                stage(znext);
+        }
 
         // column jB got the conjugate twiddles (w_M^(r (PP - j)) = w_16^r conj(w_M^(r j))): its natural output s sits at
         // butterfly output (s + 1) & 15
@@ -152,8 +174,19 @@ __global__ void __launch_bounds__(ROW_THREADS, 1)
 #pragma unroll
             for (int r = 1; r < 16; ++r) B[r] = mulw32(B[r], r); // jA = 0, jB = PP/2: w_M^(r PP/2) = w_32^r
         }
+        // ILV: twiddles | group 2 (needs the twiddled A[8..15]) | butterfly A | group 3 (needs its outputs) | butterfly B | group 4
+        // (needs its outputs) | Hermitian split and stores
+        if constexpr (ILV) {
+            if (refill) stage_after(znext, ROW_PT / 4, A);
+        }
         fft_dif<16>(A);
+        if constexpr (ILV) {
+            if (refill) stage_after(znext, ROW_PT / 2, A);
+        }
         fft_dif<16>(B);
+        if constexpr (ILV) {
+            if (refill) stage_after(znext, 3 * ROW_PT / 4, B);
+        }
         if (lt != 0) {
             const cd wb = tw3[jA]; // w_n^jA
             cd *pk = nullptr, *pm = nullptr;

@@ -49,12 +49,12 @@ template <int C> int launch_rows_long(const hpxfft_b200_plan *p, const RowDst &d
 }
 
 // ny = 16384: warp-local in-place sub-FFTs (kernels_rows_v2.cuh); HPXFFT_B200_ROWS_V1=1 selects the Stockham kernel (A/B runs)
-template <bool FAST, bool PF> int launch_rows_v2_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
+template <bool FAST, bool PF, bool ILV = false> int launch_rows_v2_t(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch)
 {
-    if (int rc = ensure_smem(rows_r2c_v2_kernel<FAST, PF>, rv2::SMEM, p->device)) return rc;
+    if (int rc = ensure_smem(rows_r2c_v2_kernel<FAST, PF, ILV>, rv2::SMEM, p->device)) return rc;
     const unsigned cap = (unsigned) (p->sm_count - p->sm_reserve > 0 ? p->sm_count - p->sm_reserve : 1);
     const unsigned grid = nrows < cap ? nrows : cap;
-    rows_r2c_v2_kernel<FAST, PF><<<grid, ROW_THREADS, rv2::SMEM, p->stream>>>(V, pitch, nrows, dst, p->tw_row);
+    rows_r2c_v2_kernel<FAST, PF, ILV><<<grid, ROW_THREADS, rv2::SMEM, p->stream>>>(V, pitch, nrows, dst, p->tw_row);
     CU(cudaGetLastError());
     return 0;
 }
@@ -124,6 +124,13 @@ bool rows_prefetch(bool dflt)
     return e ? e[0] == '1' : dflt;
 }
 
+// HPXFFT_B200_ROWS_ILV=1: ny = 16384, refill of the pencil issued in four groups between the steps of the tail (A/B runs)
+bool rows_interleaved()
+{
+    const char *e = getenv("HPXFFT_B200_ROWS_ILV");
+    return e && e[0] == '1';
+}
+
 bool rows_v1_path()
 {
     const char *e = getenv("HPXFFT_B200_ROWS_V1");
@@ -175,6 +182,7 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
     case 8192: {
         if (rows_v1_path()) return launch_rows_big<8192>(p, dst, nrows, V, pitch);
         const bool fast = dst.P == 1 && !rows_general();
+        if (rows_interleaved()) return fast ? launch_rows_v2_t<true, false, true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, false, true>(p, dst, nrows, V, pitch);
         if (rows_prefetch(false)) return fast ? launch_rows_v2_t<true, true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, true>(p, dst, nrows, V, pitch);
         return fast ? launch_rows_v2_t<true, false>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, false>(p, dst, nrows, V, pitch);
     }

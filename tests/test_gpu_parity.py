@@ -79,7 +79,9 @@ def test_r2c_rows(pkg, lib, oracle, ny):
 
 
 @pytest.mark.parametrize("env,ny", [({"HPXFFT_B200_ROWS_V1": "1"}, 16384), ({"HPXFFT_B200_ROWS_PF": "1"}, 16384),
-                                    ({"HPXFFT_B200_ROWS_GENERAL": "1"}, 16384),
+                                    ({"HPXFFT_B200_ROWS_GENERAL": "1"}, 16384), ({"HPXFFT_B200_ROWS_ILV": "1"}, 16384),
+                                    ({"HPXFFT_B200_ROWS_ILV": "1", "HPXFFT_B200_ROWS_GENERAL": "1"}, 16384),
+                                    ({"HPXFFT_B200_ROWS_ILV": "0"}, 16384),
                                     ({"HPXFFT_B200_ROWS_LONG": "1"}, 32768), ({"HPXFFT_B200_ROWS_LONG": "2"}, 32768),
                                     ({"HPXFFT_B200_ROWS_LONG": "2", "HPXFFT_B200_ROWS_GENERAL": "1"}, 32768),
                                     ({"HPXFFT_B200_ROWS_PF": "0"}, 32768),
