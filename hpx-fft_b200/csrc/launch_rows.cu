@@ -124,11 +124,13 @@ bool rows_prefetch(bool dflt)
     return e ? e[0] == '1' : dflt;
 }
 
-// HPXFFT_B200_ROWS_ILV=1: ny = 16384, refill of the pencil issued in four groups between the steps of the tail (A/B runs)
-bool rows_interleaved()
+// HPXFFT_B200_ROWS_ILV=0|1: ny = 16384, refill of the pencil issued in groups between the steps of the tail instead of one burst.
+// Default: on for the one-GPU addressing (rows 1.129 vs 1.137 ms at 16384^2, A/B/A/B in profiles/r2_x_summary.txt), off otherwise
+// (not measured with several destination ranks).
+bool rows_interleaved(bool dflt)
 {
     const char *e = getenv("HPXFFT_B200_ROWS_ILV");
-    return e && e[0] == '1';
+    return e ? e[0] == '1' : dflt;
 }
 
 bool rows_v1_path()
@@ -182,7 +184,7 @@ int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, co
     case 8192: {
         if (rows_v1_path()) return launch_rows_big<8192>(p, dst, nrows, V, pitch);
         const bool fast = dst.P == 1 && !rows_general();
-        if (rows_interleaved()) return fast ? launch_rows_v2_t<true, false, true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, false, true>(p, dst, nrows, V, pitch);
+        if (rows_interleaved(fast) && !rows_prefetch(false)) return fast ? launch_rows_v2_t<true, false, true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, false, true>(p, dst, nrows, V, pitch);
         if (rows_prefetch(false)) return fast ? launch_rows_v2_t<true, true>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, true>(p, dst, nrows, V, pitch);
         return fast ? launch_rows_v2_t<true, false>(p, dst, nrows, V, pitch) : launch_rows_v2_t<false, false>(p, dst, nrows, V, pitch);
     }
