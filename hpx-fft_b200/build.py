@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhpxfft_b200.so")
 # (source, extra defines, object suffix)
-UNITS = [("common.cu", (), ""), ("plan.cu", (), ""), ("launch_rows.cu", (), ""), ("launch_cols.cu", (), ""), ("launch_misc.cu", (), ""),
+UNITS = [("common.cu", (), ""), ("plan.cu", (), ""), ("launch_rows.cu", (), ""), ("launch_rows_long.cu", (), ""), ("launch_rows_ditc.cu", (), ""), ("launch_cols.cu", (), ""), ("launch_misc.cu", (), ""),
          ("launch_generic.cu", (), ""), ("launch_bluestein.cu", (), "")] + \
         [("launch_fused.cu", (f"HPXFFT_B200_FUSED_GROUP={g}",), f"_g{g}") for g in range(4)]
 HEADERS = ["fft_device.cuh", "layout.cuh", "kernels_rows.cuh", "kernels_rows_long.cuh", "kernels_rows_long2.cuh", "kernels_rows_dit2.cuh", "kernels_rows_ditc.cuh", "kernels_rows_v2.cuh", "kernels_cols.cuh", "kernels_misc.cuh", "kernels_generic.cuh", "kernels_bluestein.cuh",

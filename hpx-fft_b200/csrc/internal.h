@@ -108,6 +108,11 @@ namespace hpxfft_b200 {
 // all enqueue on p->stream; none synchronises
 int launch_rows(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m);
 int rows_launch_count(size_t m);
+// rows longer than one pencil (launch_rows_long.cu, launch_rows_ditc.cu) and the environment knobs they share with launch_rows.cu
+int launch_rows_longer(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, size_t m);
+int launch_rows_ditc(const hpxfft_b200_plan *p, const RowDst &dst, unsigned nrows, const cd *V, unsigned pitch, int C, bool general);
+bool rows_general();
+bool rows_prefetch(bool dflt);
 int launch_cols(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ntiles, cd *S, unsigned nx, unsigned n1,
                 unsigned n2, bool two_level, int *launches, cudaEvent_t mid = nullptr);
 int launch_cols_fused(const hpxfft_b200_plan *p, const InterView &in, const ColDst &out, unsigned ct0, unsigned ntiles);
