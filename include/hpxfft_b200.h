@@ -75,9 +75,10 @@ int hpxfft_b200_partition(size_t cy, int nranks, int rank, size_t *c0, size_t *w
  *   n_x_local : rows of this locality's slab (vector_2d::n_row)
  *   n_col     : doubles per row (vector_2d::n_col), even, >= 4
  *               supported sizes: ny = n_col-2 with ny/2 a power of two <= 65536 (ny <= 131072) and
- *               nx = n_x_local*nranks a power of two <= 2^18 take the Stockham kernels; any other even
- *               ny <= 8192 / any nx <= 8192 takes the direct-DFT kernels; larger non-powers of two are
- *               rejected with HPXFFT_B200_EINVAL
+ *               nx = n_x_local*nranks a power of two <= 2^18 take the power-of-two kernels; lengths
+ *               t * 2^a with a small odd t (rows: t < 32 and ny/2 <= 8192; columns: t <= 127) the mixed-radix
+ *               kernels; any other even ny / any nx up to 131072 Bluestein's chirp-z (<= 8192: direct DFT);
+ *               anything else is rejected with HPXFFT_B200_EINVAL
  *   rank, nranks : this locality / number of localities (hpx::get_locality_id / get_num_localities)
  *   device    : CUDA device ordinal for this rank, or -1 for the current device
  *   comm_flag : NULL (shared::loop, nranks must be 1) | "scatter" | "all_to_all"   (reference modes,
