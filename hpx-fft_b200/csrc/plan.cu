@@ -1041,10 +1041,20 @@ int hpxfft_b200_create(hpxfft_b200_plan **out, size_t n_x_local, size_t n_col, i
     const double N = (double) p->nx * (double) p->ny;
     p->meas["plan_flops"] = 2.5 * N * std::log2(N > 1 ? N : 2);
 
-    char buf[320];
+    char buf[640];
     snprintf(buf, sizeof(buf), "r2c rows: n=%zu via half-length complex Stockham m=%zu (%s), %d points/thread, paired radix-16 last pass + Hermitian split",
              p->ny, p->m, p->m <= 16 ? "register-resident" : "shared-memory pencil", p->m <= 16 ? (int) p->m : 32);
     p->row_desc = buf;
+    if (p->m == 8192)
+        p->row_desc = "r2c rows: n=16384 via half-length complex m=8192 = 16 x 512: swizzled shared-memory pencil, warp-local in-place DIF passes "
+                      "(radix 16, radix 32), paired radix-16 last pass + Hermitian split, cp.async refill of the pencil (rows_r2c_v2_kernel)";
+    else if (p->m > 8192) {
+        snprintf(buf, sizeof(buf), "r2c rows: n=%zu via half-length complex m=%zu = %zu x 8192: one persistent CTA per row runs %zu 8192-point "
+                 "sub-transforms through one shared-memory pencil, sub-spectra parked per CTA in L2, Hermitian split in the combine "
+                 "(decimation in time over sample classes: rows_dit2_kernel / rows_ditc_kernel; decimation in frequency: rows_long2_kernel / "
+                 "rows_long_kernel -- chosen per launch, launch_rows_long.cu)", p->ny, p->m, p->m / 8192, p->m / 8192);
+        p->row_desc = buf;
+    }
     if (p->rows_generic) p->row_desc = "r2c rows: direct DFT (length is not a power of two)";
     if (p->rows_mixed) {
         unsigned t, q, lg;
